@@ -1,0 +1,310 @@
+// C ABI of the B200 FELICS engine (include/felics_b200.h): contexts, container header,
+// host-memory entry points (staging copies around the device pipeline), profiling.
+#include "ctx.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace felics {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int bind_device(felics_ctx *ctx) {
+    FELICS_CUDA_TRY(cudaSetDevice(ctx->device));
+    return FELICS_OK;
+}
+
+int ensure_buffer(felics_ctx *ctx, void **buf, size_t *cap, size_t need, bool pinned_host) {
+    (void)ctx;
+    if (need <= *cap && *buf) return FELICS_OK;
+    size_t ncap = need + need / 8 + 4096;
+    if (*buf) {
+        if (pinned_host) cudaFreeHost(*buf); else cudaFree(*buf);
+        *buf = nullptr; *cap = 0;
+    }
+    void *p = nullptr;
+    cudaError_t e = pinned_host ? cudaMallocHost(&p, ncap) : cudaMalloc(&p, ncap);
+    if (e != cudaSuccess) {
+        set_error("allocation of %zu bytes failed: %s", ncap, cudaGetErrorString(e));
+        return FELICS_ERR_CUDA;
+    }
+    *buf = p; *cap = ncap;
+    return FELICS_OK;
+}
+
+StageScope::StageScope(felics_ctx *c, int st) : ctx(c), stage(st) {
+    if (!ctx->prof) return;
+    auto take = [&]() {
+        cudaEvent_t e = nullptr;
+        if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    };
+    a = take(); b = take();
+    cudaEventRecord(a, ctx->stream);
+}
+StageScope::~StageScope() {
+    if (!a) return;
+    cudaEventRecord(b, ctx->stream);
+    ctx->prof_pending.push_back({stage, a, b});
+}
+
+int profile_collect(felics_ctx *ctx) {
+    if (ctx->prof_pending.empty()) return FELICS_OK;
+    for (auto &pe : ctx->prof_pending) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(pe.b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, pe.a, pe.b);
+        if (e == cudaSuccess) ctx->stage_ms[pe.stage] += ms;
+        ctx->event_pool.push_back(pe.a);
+        ctx->event_pool.push_back(pe.b);
+    }
+    ctx->prof_pending.clear();
+    return FELICS_OK;
+}
+
+static const char *kStageNames[ST_COUNT] = {"planes", "hist", "chainscan", "tilebase", "scatter", "prefix", "grpscan",
+                                            "walk", "kfill", "code", "bitscan", "pack", "decode", "unplane"};
+
+static int check_header(const felics_header *hdr) {
+    if (!hdr) { set_error("null header"); return FELICS_ERR_INVALID_ARGUMENT; }
+    if (hdr->color_type > 1) return FELICS_ERR_INVALID_COLOR_TYPE;
+    if (hdr->pixel_depth > 1) return FELICS_ERR_INVALID_PIXEL_DEPTH;
+    return FELICS_OK;
+}
+
+}  // namespace felics
+
+using namespace felics;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char *felics_version(void) { return "felics_b200 0.1 (sm_100a)"; }
+const char *felics_last_error(void) { return g_err; }
+
+int felics_ctx_create(int device, felics_ctx **out) {
+    if (!out) return FELICS_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device: %s (this engine has no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return FELICS_ERR_CUDA;
+    }
+    if (device < 0) FELICS_CUDA_TRY(cudaGetDevice(&device));
+    if (device >= count) { set_error("device %d out of range (%d devices)", device, count); return FELICS_ERR_INVALID_ARGUMENT; }
+    FELICS_CUDA_TRY(cudaSetDevice(device));
+    felics_ctx *ctx = new (std::nothrow) felics_ctx();
+    if (!ctx) return FELICS_ERR_CUDA;
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return FELICS_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return FELICS_OK;
+}
+
+void felics_ctx_destroy(felics_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &pe : ctx->prof_pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->staging_in) cudaFree(ctx->staging_in);
+    if (ctx->staging_out) cudaFree(ctx->staging_out);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int felics_ctx_set_stream(felics_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return FELICS_ERR_INVALID_ARGUMENT;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return FELICS_OK;
+}
+
+// format.rs:63-84 (check order: magic, colour, depth, then the two u32)
+int felics_read_header(const uint8_t *buf, size_t len, felics_header *out) {
+    if (!out || (!buf && len)) return FELICS_ERR_INVALID_ARGUMENT;
+    if (len < 4) return FELICS_ERR_IO;
+    if (memcmp(buf, "FLCS", 4) != 0) return FELICS_ERR_INVALID_SIGNATURE;
+    if (len < 5) return FELICS_ERR_IO;
+    if (buf[4] > 1) return FELICS_ERR_INVALID_COLOR_TYPE;
+    if (len < 6) return FELICS_ERR_IO;
+    if (buf[5] > 1) return FELICS_ERR_INVALID_PIXEL_DEPTH;
+    if (len < FELICS_HEADER_BYTES) return FELICS_ERR_IO;
+    out->color_type = buf[4];
+    out->pixel_depth = buf[5];
+    out->width = ((uint32_t)buf[6] << 24) | ((uint32_t)buf[7] << 16) | ((uint32_t)buf[8] << 8) | buf[9];
+    out->height = ((uint32_t)buf[10] << 24) | ((uint32_t)buf[11] << 16) | ((uint32_t)buf[12] << 8) | buf[13];
+    return FELICS_OK;
+}
+
+// format.rs:51-61
+int felics_write_header(const felics_header *hdr, uint8_t *o) {
+    int rc = check_header(hdr);
+    if (rc) return rc;
+    if (!o) return FELICS_ERR_INVALID_ARGUMENT;
+    memcpy(o, "FLCS", 4);
+    o[4] = hdr->color_type; o[5] = hdr->pixel_depth;
+    o[6] = (uint8_t)(hdr->width >> 24); o[7] = (uint8_t)(hdr->width >> 16); o[8] = (uint8_t)(hdr->width >> 8); o[9] = (uint8_t)hdr->width;
+    o[10] = (uint8_t)(hdr->height >> 24); o[11] = (uint8_t)(hdr->height >> 16); o[12] = (uint8_t)(hdr->height >> 8); o[13] = (uint8_t)hdr->height;
+    return FELICS_OK;
+}
+
+size_t felics_pixel_bytes(const felics_header *hdr) {
+    if (!hdr) return 0;
+    return (size_t)hdr->width * hdr->height * (hdr->color_type ? 3 : 1) * (hdr->pixel_depth ? 2 : 1);
+}
+
+size_t felics_compress_bound(const felics_header *hdr) {
+    if (!hdr) return 0;
+    size_t npix = (size_t)hdr->width * hdr->height, nch = hdr->color_type ? 3 : 1;
+    // marker 2 + unary (max_context >> 0) + 1 + k bits per sample, 64 raw bits per channel
+    size_t per = hdr->pixel_depth ? 131100 : 520;
+    return FELICS_HEADER_BYTES + nch * 8 + (npix * nch * per + 7) / 8 + 8;
+}
+
+int felics_compress_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header *hdr, uint8_t *d_arena,
+                                 size_t arena_cap, uint64_t *offsets) {
+    if (!ctx || !offsets || (n && (!d_arena))) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = check_header(hdr);
+    if (rc) return rc;
+    if ((rc = bind_device(ctx))) return rc;
+    offsets[0] = 0;
+    if (n == 0) return FELICS_OK;
+    if (!d_pixels && felics_pixel_bytes(hdr)) { set_error("null pixels"); return FELICS_ERR_INVALID_ARGUMENT; }
+    return encode_batch_device(ctx, n, d_pixels, *hdr, d_arena, nullptr, arena_cap, offsets);
+}
+
+int felics_compress_device(felics_ctx *ctx, const void *d_pixels, const felics_header *hdr, uint8_t *d_out, size_t cap, size_t *out_len) {
+    uint64_t off[2] = {0, 0};
+    int rc = felics_compress_batch_device(ctx, 1, d_pixels, hdr, d_out, cap, off);
+    if (out_len) *out_len = (size_t)off[1];
+    return rc;
+}
+
+int felics_compress_batch(felics_ctx *ctx, size_t n, const void *pixels, const felics_header *hdr, uint8_t *arena, size_t arena_cap,
+                          uint64_t *offsets) {
+    if (!ctx || !offsets || (n && !arena)) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = check_header(hdr);
+    if (rc) return rc;
+    if ((rc = bind_device(ctx))) return rc;
+    offsets[0] = 0;
+    if (n == 0) return FELICS_OK;
+    size_t in_bytes = felics_pixel_bytes(hdr) * n;
+    if (in_bytes && !pixels) { set_error("null pixels"); return FELICS_ERR_INVALID_ARGUMENT; }
+    if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, in_bytes + 16))) return rc;
+    if (in_bytes) FELICS_CUDA_TRY(cudaMemcpyAsync(ctx->staging_in, pixels, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return encode_batch_device(ctx, n, ctx->staging_in, *hdr, nullptr, arena, arena_cap, offsets);
+}
+
+int felics_compress(felics_ctx *ctx, const void *pixels, const felics_header *hdr, uint8_t *out, size_t cap, size_t *out_len) {
+    uint64_t off[2] = {0, 0};
+    int rc = felics_compress_batch(ctx, 1, pixels, hdr, out, cap, off);
+    if (out_len) *out_len = (size_t)off[1];
+    return rc;
+}
+
+int felics_decompress_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets, const felics_header *hdr,
+                                   void *d_pixels_out, int *status) {
+    if (!ctx || !offsets || !status || (n && !d_arena)) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = check_header(hdr);
+    if (rc) return rc;
+    if ((rc = bind_device(ctx))) return rc;
+    if (n == 0) return FELICS_OK;
+    return decode_batch_device(ctx, n, d_arena, offsets, *hdr, d_pixels_out, status);
+}
+
+int felics_decompress_batch(felics_ctx *ctx, size_t n, const uint8_t *arena, const uint64_t *offsets, const felics_header *hdr,
+                            void *pixels_out, int *status) {
+    if (!ctx || !offsets || !status || (n && !arena)) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = check_header(hdr);
+    if (rc) return rc;
+    if ((rc = bind_device(ctx))) return rc;
+    if (n == 0) return FELICS_OK;
+    size_t in_bytes = (size_t)offsets[n];
+    size_t out_bytes = felics_pixel_bytes(hdr) * n;
+    if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, in_bytes + 16))) return rc;
+    if ((rc = ensure_buffer(ctx, &ctx->staging_out, &ctx->staging_out_cap, out_bytes + 16))) return rc;
+    FELICS_CUDA_TRY(cudaMemcpyAsync(ctx->staging_in, arena, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = decode_batch_device(ctx, n, (const uint8_t *)ctx->staging_in, offsets, *hdr, ctx->staging_out, status);
+    // images that decoded are returned even when others failed
+    if (out_bytes && pixels_out && (rc == FELICS_OK || rc > FELICS_ERR_CUDA || rc == FELICS_ERR_CORRUPT)) {
+        FELICS_CUDA_TRY(cudaMemcpyAsync(pixels_out, ctx->staging_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        FELICS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return rc;
+}
+
+int felics_decompress(felics_ctx *ctx, const uint8_t *fel, size_t len, void *pixels_out, size_t cap, felics_header *hdr_out) {
+    felics_header hdr;
+    int rc = felics_read_header(fel, len, &hdr);
+    if (rc) return rc;
+    if (hdr_out) *hdr_out = hdr;
+    uint64_t npix = (uint64_t)hdr.width * hdr.height;
+    if (npix > 0xffffffffull) return FELICS_ERR_INVALID_DIMENSIONS;   // checked_mul (compression.rs:176-180)
+    size_t need = felics_pixel_bytes(&hdr);
+    if (need > cap) { set_error("pixel buffer too small: need %zu", need); return FELICS_ERR_BUFFER_TOO_SMALL; }
+    uint64_t off[2] = {0, (uint64_t)len};
+    int status = 0;
+    return felics_decompress_batch(ctx, 1, fel, off, &hdr, pixels_out, &status);
+}
+
+int felics_decompress_device(felics_ctx *ctx, const uint8_t *d_fel, size_t len, void *d_pixels_out, size_t cap, felics_header *hdr_out) {
+    if (!ctx || !d_fel) return FELICS_ERR_INVALID_ARGUMENT;
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    uint8_t hb[FELICS_HEADER_BYTES];
+    size_t hl = len < FELICS_HEADER_BYTES ? len : FELICS_HEADER_BYTES;
+    if (hl) FELICS_CUDA_TRY(cudaMemcpy(hb, d_fel, hl, cudaMemcpyDeviceToHost));
+    felics_header hdr;
+    if ((rc = felics_read_header(hb, hl, &hdr))) return rc;
+    if (hdr_out) *hdr_out = hdr;
+    uint64_t npix = (uint64_t)hdr.width * hdr.height;
+    if (npix > 0xffffffffull) return FELICS_ERR_INVALID_DIMENSIONS;
+    size_t need = felics_pixel_bytes(&hdr);
+    if (need > cap) { set_error("pixel buffer too small: need %zu", need); return FELICS_ERR_BUFFER_TOO_SMALL; }
+    uint64_t off[2] = {0, (uint64_t)len};
+    int status = 0;
+    return felics_decompress_batch_device(ctx, 1, d_fel, off, &hdr, d_pixels_out, &status);
+}
+
+int felics_profile_enable(felics_ctx *ctx, int on) {
+    if (!ctx) return FELICS_ERR_INVALID_ARGUMENT;
+    ctx->prof = on != 0;
+    return FELICS_OK;
+}
+int felics_profile_reset(felics_ctx *ctx) {
+    if (!ctx) return FELICS_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < ST_COUNT; i++) { ctx->stage_ms[i] = 0; ctx->stage_launches[i] = 0; }
+    ctx->total_launches = 0;
+    return FELICS_OK;
+}
+int felics_profile_stage_count(void) { return ST_COUNT; }
+const char *felics_profile_stage_name(int stage) { return stage >= 0 && stage < ST_COUNT ? kStageNames[stage] : ""; }
+double felics_profile_stage_ms(felics_ctx *ctx, int stage) { return ctx && stage >= 0 && stage < ST_COUNT ? ctx->stage_ms[stage] : 0.0; }
+uint64_t felics_profile_stage_launches(felics_ctx *ctx, int stage) { return ctx && stage >= 0 && stage < ST_COUNT ? ctx->stage_launches[stage] : 0; }
+uint64_t felics_profile_total_launches(felics_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
+
+// Debug aid for the parity tests (not in the public header): copy the per-pixel code
+// records of the last encode call (length in bits 31..22) to the host.
+int felics_debug_last_records(felics_ctx *ctx, uint32_t *out, size_t count) {
+    if (!ctx || !ctx->dbg_rec || count > ctx->dbg_rec_count) return FELICS_ERR_INVALID_ARGUMENT;
+    FELICS_CUDA_TRY(cudaMemcpy(out, ctx->dbg_rec, count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return FELICS_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

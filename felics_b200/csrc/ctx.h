@@ -1,0 +1,98 @@
+// Internal context of the B200 FELICS engine (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+#include <string>
+
+#include "../../include/felics_b200.h"
+
+namespace felics {
+
+// Pipeline stages that get their own CUDA-event bracket when profiling is on.
+enum Stage : int {
+    ST_PLANES = 0,   // pixels -> i16 planes (+ YCoCg-R for RGB)
+    ST_HIST,         // per-tile context histograms of out-of-range pixels
+    ST_CHAINSCAN,    // per-plane chain sizes / bases
+    ST_TILEBASE,     // per-tile, per-context scatter bases
+    ST_SCATTER,      // stable grouping of residuals by context
+    ST_PREFIX,       // per-32-block code-cost prefix sums for the 6 k candidates
+    ST_GRPSCAN,      // scan of the per-1024 group totals
+    ST_WALK,         // halving-epoch walk (the sequential part of the estimator)
+    ST_KFILL,        // k per out-of-range pixel
+    ST_CODE,         // code word + length per pixel, bits per tile
+    ST_BITSCAN,      // bit offsets: tiles -> planes -> images
+    ST_PACK,         // MSB-first bit packing
+    ST_DECODE,       // bit-serial decode, one stream per warp
+    ST_UNPLANE,      // i16 planes -> pixels (+ inverse YCoCg-R), range checks
+    ST_COUNT
+};
+
+struct ProfEntry { int stage; cudaEvent_t a, b; };
+
+void set_error(const char *fmt, ...);
+
+}  // namespace felics
+
+struct felics_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+
+    void *scratch = nullptr;      // device scratch, grown on demand
+    size_t scratch_cap = 0;
+    void *staging_in = nullptr;   // device staging for host-memory entry points
+    size_t staging_in_cap = 0;
+    void *staging_out = nullptr;
+    size_t staging_out_cap = 0;
+    void *pinned = nullptr;       // small pinned host buffer for read-backs
+    size_t pinned_cap = 0;
+
+    bool prof = false;
+    std::vector<felics::ProfEntry> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[felics::ST_COUNT] = {0};
+    uint64_t stage_launches[felics::ST_COUNT] = {0};
+    uint64_t total_launches = 0;
+
+    // debug: device pointer / count of the per-pixel code records of the last encode
+    const uint32_t *dbg_rec = nullptr;
+    size_t dbg_rec_count = 0;
+};
+
+namespace felics {
+
+#define FELICS_CUDA_TRY(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            felics::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return FELICS_ERR_CUDA;                                                        \
+        }                                                                                  \
+    } while (0)
+
+int ensure_buffer(felics_ctx *ctx, void **buf, size_t *cap, size_t need, bool pinned_host = false);
+int bind_device(felics_ctx *ctx);
+
+// RAII-less stage bracket: begin() records an event if profiling, end() likewise.
+struct StageScope {
+    felics_ctx *ctx;
+    int stage;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(felics_ctx *c, int st);
+    ~StageScope();
+    void launched(int n = 1) { ctx->stage_launches[stage] += n; ctx->total_launches += n; }
+};
+int profile_collect(felics_ctx *ctx);  // after a stream sync: fold pending events into stage_ms
+
+// encode.cu
+int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
+                        uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
+// decode.cu
+int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
+                        const felics_header &hdr, void *d_pixels_out, int *status_host);
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace felics

@@ -1,0 +1,101 @@
+// Device helpers shared by the encode and decode kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace felics {
+
+constexpr int TILE = 4096;          // pixels per tile (one thread block)
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_WARPS = TILE_THREADS / 32;
+constexpr int WARP_PIX = TILE / TILE_WARPS;   // 512 consecutive pixels per warp
+constexpr int WARP_ITERS = WARP_PIX / 32;     // 16 rounds of 32 consecutive pixels
+constexpr int NBIN = 512;           // contexts 0..510 (traits.rs:29: MAX_CONTEXT = 2*255) padded to 512
+constexpr int CHUNK_TILES = 64;     // tiles per histogram chunk
+constexpr int GROUP = 1024;         // grouped elements per prefix group (32 blocks of 32)
+constexpr uint32_t HALVE_AT = 1024; // traits.rs:31 COUNT_SCALING = Some(1024)
+constexpr int NK = 6;               // traits.rs:27 K_VALUES = [0..5]
+constexpr uint32_t PAD_E = 0xFFFFu; // marks padding slots of the grouped residual array
+
+// Neighbour geometry + classification of pixel i of a row-major plane
+// (misc.rs:6-24, compression.rs:118-145).  cls: 0 in-range, 1 above, 2 below.
+struct PixelClass {
+    int delta;  // context H - L
+    int cls;
+    int val;    // P-L (in-range) | P-H-1 (above) | L-P-1 (below)
+    int lo;
+};
+
+__device__ __forceinline__ PixelClass classify_pixel(const int16_t *__restrict__ pl, uint32_t i, uint32_t w) {
+    uint32_t y = i / w;
+    uint32_t x = i - y * w;
+    uint32_t a, b;
+    if (x > 0 && y > 0) { a = i - 1; b = i - w; }            // left, up
+    else if (y == 0) { a = i - 1; b = i - 2; }               // first row (x >= 2 because i >= 2)
+    else if (y >= 2) { a = i - w; b = i - 2 * w; }           // first column
+    else { a = i - w; b = i - w + 1; }                       // (0,1): up, up-right
+    int p = pl[i], v1 = pl[a], v2 = pl[b];
+    int h = max(v1, v2), l = min(v1, v2);
+    PixelClass r;
+    r.delta = h - l;
+    r.lo = l;
+    if (p < l) { r.cls = 2; r.val = l - p - 1; }
+    else if (p > h) { r.cls = 1; r.val = p - h - 1; }
+    else { r.cls = 0; r.val = p - l; }
+    return r;
+}
+
+// Phased-in code of v in [0, n-1] (phase_in_coding.rs:23-84): returns the code value, sets len.
+// long codeword = (x - right_p)/2 + right_p in m bits followed by (x - right_p)&1  ==  x + right_p in m+1 bits.
+__device__ __forceinline__ uint32_t phase_in_code(uint32_t n, uint32_t v, int &len) {
+    int m = 31 - __clz(n);
+    uint32_t left_p = n - (1u << m);
+    uint32_t right_p = (2u << m) - n;
+    uint32_t x = v + n - left_p;
+    if (x >= n) x -= n;
+    if (x < right_p) { len = m; return x; }
+    len = m + 1;
+    return x + right_p;
+}
+
+// k of a counter row: `<=` scan, ties go to the largest index (parameter_selection.rs:78-83).
+__device__ __forceinline__ int argmin_last(const uint32_t v[NK]) {
+    uint32_t best = v[0];
+    int bi = 0;
+#pragma unroll
+    for (int k = 1; k < NK; k++)
+        if (v[k] <= best) { best = v[k]; bi = k; }
+    return bi;
+}
+
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// OR `n` (1..32) bits of val, MSB first, at absolute bit position `bit` of a word
+// buffer whose words hold the stream big-endian-in-register (bit 31 = first bit).
+__device__ __forceinline__ void put_bits_smem(uint32_t *buf, uint32_t bit, uint32_t val, int n) {
+    uint32_t wi = bit >> 5, sh = bit & 31;
+    uint32_t left = val << (32 - n);
+    atomicOr(&buf[wi], left >> sh);
+    if (sh + n > 32) atomicOr(&buf[wi + 1], left << (32 - sh));
+}
+// Same on the global arena, whose memory is the byte stream itself (so byte-swap).
+__device__ __forceinline__ void put_bits_global(uint32_t *arena, uint64_t bit, uint32_t val, int n) {
+    uint64_t wi = bit >> 5;
+    uint32_t sh = (uint32_t)(bit & 31);
+    uint32_t left = val << (32 - n);
+    uint32_t hi = left >> sh;
+    if (hi) atomicOr(&arena[wi], bswap32(hi));
+    if (sh + n > 32) {
+        uint32_t lo = left << (32 - sh);
+        if (lo) atomicOr(&arena[wi + 1], bswap32(lo));
+    }
+}
+
+// Per-pixel code record (u32): bits 31..22 = length (0..1023), bits 21..0 = payload.
+//   length <= REC_SHORT_MAX: payload is the whole code word, right aligned.
+//   otherwise (out-of-range pixel with a long unary run): payload =
+//     above(1) << 17 | k(3) << 14 | rem(5) << 9 | q(9)
+constexpr int REC_SHORT_MAX = 22;
+__device__ __forceinline__ uint32_t rec_len(uint32_t rec) { return rec >> 22; }
+
+}  // namespace felics
