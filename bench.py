@@ -305,13 +305,15 @@ def run_ours(args):
     dec_steps = 1 if args.workload != "tiles" else min(args.steps, 3)
     codec.profile(True)
     t0 = time.perf_counter()
-    for _ in range(dec_steps):
-        status = codec.decompress_batch_device(n_img, d_out.data_ptr(), offsets, hdr, d_pix_out.data_ptr())
-    torch.cuda.synchronize(dev)
+    lossless = True
+    if args.decode:
+        for _ in range(dec_steps):
+            status = codec.decompress_batch_device(n_img, d_out.data_ptr(), offsets, hdr, d_pix_out.data_ptr())
+        torch.cuda.synchronize(dev)
+        lossless = bool((not status.any()) and torch.equal(d_pix_out, d_in.view(-1)))
     dec_wall = time.perf_counter() - t0
     dec_stage = codec.stage_times()
     codec.profile(False)
-    lossless = bool((not status.any()) and torch.equal(d_pix_out, d_in.view(-1)))
 
     def reduce_max(x):
         if world == 1:
@@ -387,8 +389,8 @@ def run_ours(args):
                     "ms_per_step": tot_e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "decode": {"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": ok_all,
-                       "wall_ms": 1e3 * dec_wall / dec_steps},
+            "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": ok_all,
+                        "wall_ms": 1e3 * dec_wall / dec_steps} if args.decode else None),
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
             "parity": parity,
             "wall_s_timed_region": wall_dev,
@@ -408,6 +410,7 @@ def main():
     ap.add_argument("--workload", choices=["image", "tiles"], default="image")
     ap.add_argument("--tiles", type=int, default=2048, help="tiles per GPU for --workload tiles")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check of the timed output")
+    ap.add_argument("--no-decode", dest="decode", action="store_false", help="skip the (slow, single-stream) decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
