@@ -216,14 +216,17 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const int16_t *__restr
 // prefix: one block per group of 1024 grouped elements (32 blocks of 32).
 // fine[g] = {U01, U23, U45, e}: inclusive prefix, within the 32-block, of the code cost
 // (e >> k) + 1 + k for k = 0..5, two 16-bit lanes per word (32 * 516 < 65536).
-// blk_local[blk][k]: exclusive prefix of the block totals inside the group.
-// grp_tot[grp][k]: totals of the group (scanned by k_grpscan).
+// blk_rec[blk] (16 x u32): [0..5] cost prefix T at the block start, [8..13] T at the block
+// end -- local to the group here, made global by k_blkfinal.
+// grp_tot[grp][k]: totals of the group (scanned by k_grpscan1/2).
 // All prefix sums are mod 2^32 over the whole grouped array; only differences inside a
 // chain are ever used, so chain boundaries need no segmentation.
 // ------------------------------------------------------------------------------------
+constexpr int BLK_REC = 16;
+
 __global__ void __launch_bounds__(GROUP) k_prefix(const uint16_t *__restrict__ e_grp, uint32_t cap, uint32_t gpp,
                                                   const uint32_t *__restrict__ plane_used, uint4 *__restrict__ fine,
-                                                  uint32_t *__restrict__ blk_local, uint32_t *__restrict__ grp_tot) {
+                                                  uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ grp_tot) {
     __shared__ uint32_t tot[32][NK];
     uint32_t grp = blockIdx.x;
     uint32_t p = grp / gpp;
@@ -263,67 +266,105 @@ __global__ void __launch_bounds__(GROUP) k_prefix(const uint16_t *__restrict__ e
                 uint32_t n = __shfl_up_sync(0xffffffffu, s, o);
                 if (lane >= (uint32_t)o) s += n;
             }
-            blk_local[blk * 8 + k] = s - v;
+            blk_rec[blk * BLK_REC + k] = s - v;
+            blk_rec[blk * BLK_REC + 8 + k] = s;
             if (lane == 31) grp_tot[(size_t)grp * 8 + k] = s;
         }
     }
 }
 
-// grpscan: single block, exclusive scan (mod 2^32) of the group totals, in place.
-__global__ void __launch_bounds__(1024) k_grpscan(uint32_t *__restrict__ grp_tot, uint32_t ngroups) {
+// Exclusive scan (mod 2^32) of `n` records of 8 x u32 (6 used), in place, by one thread block
+// per 1024 records; block totals go to `tot_out` (nullptr: not needed).
+__device__ __forceinline__ void block_scan_records(uint32_t *__restrict__ rec, uint32_t n, uint32_t base_idx,
+                                                   uint32_t carry_in[NK], uint32_t total_out[NK], uint32_t (*wsum)[NK]) {
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t idx = base_idx + threadIdx.x;
+    uint32_t v[NK], s[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        v[k] = idx < n ? rec[(size_t)idx * 8 + k] : 0;
+        s[k] = v[k];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, s[k], o);
+            if (lane >= (uint32_t)o) s[k] += t;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) wsum[wid][k] = s[k];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            uint32_t x = wsum[lane][k], y = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, y, o);
+                if (lane >= (uint32_t)o) y += t;
+            }
+            wsum[lane][k] = y - x;  // exclusive over warps
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        uint32_t excl = carry_in[k] + wsum[wid][k] + s[k] - v[k];
+        if (idx < n) rec[(size_t)idx * 8 + k] = excl;
+        total_out[k] = excl + v[k];  // meaningful in the last thread
+    }
+}
+
+// level 1: every block scans 1024 group totals; its total goes to super_tot
+__global__ void __launch_bounds__(1024) k_grpscan1(uint32_t *__restrict__ grp_tot, uint32_t ngroups, uint32_t *__restrict__ super_tot) {
+    __shared__ uint32_t wsum[32][NK];
+    uint32_t carry[NK] = {0, 0, 0, 0, 0, 0}, total[NK];
+    block_scan_records(grp_tot, ngroups, blockIdx.x * 1024u, carry, total, wsum);
+    if (threadIdx.x == 1023) {
+#pragma unroll
+        for (int k = 0; k < NK; k++) super_tot[(size_t)blockIdx.x * 8 + k] = total[k];
+    }
+}
+// level 2: one block scans the super totals
+__global__ void __launch_bounds__(1024) k_grpscan2(uint32_t *__restrict__ super_tot, uint32_t nsuper) {
     __shared__ uint32_t wsum[32][NK];
     __shared__ uint32_t carry_s[NK];
-    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x < NK) carry_s[threadIdx.x] = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < ngroups; base += 1024) {
-        uint32_t gidx = base + threadIdx.x;
-        uint32_t v[NK], s[NK];
+    for (uint32_t base = 0; base < nsuper; base += 1024) {
+        uint32_t carry[NK], total[NK];
 #pragma unroll
-        for (int k = 0; k < NK; k++) {
-            v[k] = gidx < ngroups ? grp_tot[(size_t)gidx * 8 + k] : 0;
-            s[k] = v[k];
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-#pragma unroll
-            for (int k = 0; k < NK; k++) {
-                uint32_t n = __shfl_up_sync(0xffffffffu, s[k], o);
-                if (lane >= (uint32_t)o) s[k] += n;
-            }
-        }
-        if (lane == 31) {
-#pragma unroll
-            for (int k = 0; k < NK; k++) wsum[wid][k] = s[k];
-        }
-        __syncthreads();
-        if (wid == 0) {
-#pragma unroll
-            for (int k = 0; k < NK; k++) {
-                uint32_t x = wsum[lane][k], y = x;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    uint32_t n = __shfl_up_sync(0xffffffffu, y, o);
-                    if (lane >= (uint32_t)o) y += n;
-                }
-                wsum[lane][k] = y - x;  // exclusive over warps
-            }
-        }
-        __syncthreads();
-        uint32_t chunk_tot_k[NK];
-#pragma unroll
-        for (int k = 0; k < NK; k++) {
-            uint32_t excl = carry_s[k] + wsum[wid][k] + s[k] - v[k];
-            if (gidx < ngroups) grp_tot[(size_t)gidx * 8 + k] = excl;
-            chunk_tot_k[k] = excl + v[k];  // inclusive at this thread
-        }
+        for (int k = 0; k < NK; k++) carry[k] = carry_s[k];
+        block_scan_records(super_tot, nsuper, base, carry, total, wsum);
         __syncthreads();
         if (threadIdx.x == 1023) {
 #pragma unroll
-            for (int k = 0; k < NK; k++) carry_s[k] = chunk_tot_k[k];
+            for (int k = 0; k < NK; k++) carry_s[k] = total[k];
         }
         __syncthreads();
     }
+}
+// make the block records global: add the group's and the super-group's exclusive prefix.
+// One thread per 16-byte quarter of a record.
+__global__ void __launch_bounds__(256) k_blkfinal(uint4 *__restrict__ blk_rec4, const uint32_t *__restrict__ grp_pre,
+                                                  const uint32_t *__restrict__ super_pre, const uint32_t *__restrict__ plane_used,
+                                                  uint32_t gpp, size_t nquarters) {
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nquarters) return;
+    size_t blk = q >> 2;
+    uint32_t part = (uint32_t)(q & 3);
+    uint32_t grp = (uint32_t)(blk >> 5);
+    uint32_t p = grp / gpp;
+    if ((grp - p * gpp) * GROUP >= plane_used[p]) return;
+    const uint32_t *gp = grp_pre + (size_t)grp * 8, *sp = super_pre + (size_t)(grp >> 10) * 8;
+    uint4 r = blk_rec4[q];
+    if ((part & 1) == 0) { r.x += gp[0] + sp[0]; r.y += gp[1] + sp[1]; r.z += gp[2] + sp[2]; r.w += gp[3] + sp[3]; }
+    else { r.x += gp[4] + sp[4]; r.y += gp[5] + sp[5]; }
+    blk_rec4[q] = r;
 }
 
 // ------------------------------------------------------------------------------------
@@ -331,150 +372,295 @@ __global__ void __launch_bounds__(1024) k_grpscan(uint32_t *__restrict__ grp_tot
 // base[k] = S[k] - T(cur)[k] (mod 2^32), T = global exclusive cost prefix, cur = first
 // element of the current epoch; the counters before element t are base + T(t).
 // Epoch i is recorded as (first element, base) for k_kfill.
+// Per window of 32 blocks (1024 elements) the fine records (16 KB) and block records (2 KB)
+// are prefetched into shared memory with cp.async, double buffered.
 // ------------------------------------------------------------------------------------
 struct WalkArgs {
     const uint4 *fine;
-    const uint32_t *blk_local;
-    const uint32_t *grp_pre;
+    const uint4 *blk_rec4;  // 4 x uint4 per 32-block
     const uint32_t *chain_count;
     const uint32_t *chain_base;
     const uint32_t *live;
     uint32_t *counters;     // [0] live count, [1] queue head, [2] error flags
-    uint32_t *ep_start;     // global element index of the first element of each epoch
-    uint32_t *ep_base;      // [epoch][8]
+    uint4 *ep_rec;          // 2 x uint4 per epoch: {base0..3}, {base4, base5, first element (global index), 0}
     uint32_t *blk_epoch;    // epoch in effect at the start of each 32-block
     uint32_t cap;           // grouped elements per plane
     uint32_t epcap;         // epoch records per plane
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+// register-array element by a runtime index without forcing the array into local memory
+__device__ __forceinline__ uint32_t sel6(const uint32_t v[NK], uint32_t i) {
+    uint32_t r = v[0];
+    r = i == 1 ? v[1] : r; r = i == 2 ? v[2] : r; r = i == 3 ? v[3] : r; r = i == 4 ? v[4] : r; r = i == 5 ? v[5] : r;
+    return r;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void unpack6(const uint4 &f, uint32_t U[NK]) {
+    U[0] = f.x & 0xffffu; U[1] = f.x >> 16; U[2] = f.y & 0xffffu; U[3] = f.y >> 16; U[4] = f.z & 0xffffu; U[5] = f.z >> 16;
+}
+
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// ---- epoch walk building blocks ------------------------------------------------------------------
+struct WalkWin {             // constants of the current window (32 blocks = 1024 elements)
+    const uint4 *sfine;      // shared: fine records of the window
+    const uint4 *sblk;       // shared: block records of the window (4 x uint4 per block)
+    uint32_t wb;             // first block of the window (chain-relative)
+    bool valid;              // my block exists
+    uint32_t incl[NK];       // cost prefix at the END of my block
+};
+struct WalkSt {              // state of the walk along one chain
+    uint32_t base[NK];       // counters before element t are base + T(t)
+    uint32_t cur;            // chain-relative first element of the current epoch
+    int curblk;              // block (window-relative) holding `cur`; <= 0 when at/before the window start
+    uint32_t blkmask;        // lanes (= blocks) at or after curblk
+    uint32_t lanemask;       // lanes (= elements) at or after `cur` inside curblk
+    uint32_t nep;            // epochs recorded so far
+    uint32_t my_epoch;       // epoch in effect at the start of my block
+    bool overflow;
+};
+struct WalkChain {
+    uint4 *rec;
+    uint32_t ep_room, gbase32, count, lane;
+};
+
+// a halving happened at element h of block B: record the new epoch
+__device__ __forceinline__ bool commit_epoch(WalkSt &s, const WalkWin &w, const WalkChain &c, int B, int h) {
+    s.cur = (w.wb + (uint32_t)B) * 32u + (uint32_t)h + 1u;
+    s.curblk = B + (h == 31 ? 1 : 0);
+    s.blkmask = s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk);
+    s.lanemask = 0xffffffffu << ((uint32_t)(h + 1) & 31u);
+    if (s.nep + 1 < c.ep_room) {
+        if (c.lane == 0) {
+            c.rec[2 * s.nep] = make_uint4(s.base[0], s.base[1], s.base[2], s.base[3]);
+            c.rec[2 * s.nep + 1] = make_uint4(s.base[4], s.base[5], c.gbase32 + s.cur, 0u);
+        }
+    } else {
+        s.overflow = true;
+    }
+    s.nep++;
+    if ((int)c.lane > B) s.my_epoch++;
+    return s.cur >= c.count;
+}
+
+// per-lane: all six counters after MY element of block B, their minimum, and the base the next
+// epoch would have if the halving fell on my element (parameter_selection.rs:58-63, re-based)
+__device__ __forceinline__ int32_t element_state(const WalkSt &s, const WalkWin &w, int B, uint32_t lane, uint32_t nb[NK],
+                                                 uint32_t v[NK], uint32_t &e_out) {
+    const uint4 f = w.sfine[B * 32 + lane];
+    const uint4 e0 = w.sblk[B * 4], e1 = w.sblk[B * 4 + 1];
+    const uint32_t cps[NK] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y};
+    uint32_t U[NK];
+    unpack6(f, U);
+    e_out = f.w;
+    int32_t mn = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        uint32_t T = cps[k] + U[k];      // cost prefix including my element
+        v[k] = s.base[k] + T;            // counter after my element's update
+        mn = min(mn, (int32_t)v[k]);
+        nb[k] = (v[k] >> 1) - T;
+    }
+    return mn;
+}
+
+// Fast path: the block is chosen by looking at the candidate counters KA, KB only (fixed registers);
+// the element test then uses all six counters, which both finds the halving element and proves
+// that no other counter is slower.  Returns 0: no halving left in this window, 1: needs the generic
+// path (another counter passes 1024 later than the candidates), 2: chain finished.
+template <int KA, int KB>
+__device__ __forceinline__ int fast_epochs(WalkSt &s, const WalkWin &w, const WalkChain &c) {
+    for (;;) {
+        bool ok = w.valid && ((int32_t)(s.base[KA] + w.incl[KA]) > (int32_t)HALVE_AT);
+        if (KA != KB) ok = ok && ((int32_t)(s.base[KB] + w.incl[KB]) > (int32_t)HALVE_AT);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok) & s.blkmask;
+        if (!m) return 0;
+        const int B = __ffs(m) - 1;
+        uint32_t nb[NK], v[NK], e;
+        const int32_t mn = element_state(s, w, B, c.lane, nb, v, e);
+        uint32_t fm = __ballot_sync(0xffffffffu, mn > (int32_t)HALVE_AT);
+        if (B == s.curblk) fm &= s.lanemask;
+        if (!fm) return 1;
+        const int h = __ffs(fm) - 1;
+#pragma unroll
+        for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, nb[k], h);
+        if (commit_epoch(s, w, c, B, h)) return 2;
+    }
+}
+
+// One epoch on all six counters.  Returns 0: no halving left in this window, 2: chain finished,
+// 3: internal error, 4: epoch done (bmask = the counters that passed 1024 last).
+__device__ __forceinline__ int generic_epoch(WalkSt &s, const WalkWin &w, const WalkChain &c, uint32_t &bmask) {
+    bool ok = w.valid;
+#pragma unroll
+    for (int k = 0; k < NK; k++) ok = ok && ((int32_t)(s.base[k] + w.incl[k]) > (int32_t)HALVE_AT);
+    const uint32_t m = __ballot_sync(0xffffffffu, ok) & s.blkmask;
+    if (!m) return 0;
+    const int B = __ffs(m) - 1;
+    uint32_t nb[NK], v[NK], e;
+    const int32_t mn = element_state(s, w, B, c.lane, nb, v, e);
+    uint32_t fm = __ballot_sync(0xffffffffu, mn > (int32_t)HALVE_AT);
+    if (B == s.curblk) fm &= s.lanemask;
+    if (!fm) return 3;   // cannot happen: the block's last element passes
+    const int h = __ffs(fm) - 1;
+    // binding counters: still <= 1024 before the halving element's update
+    uint32_t bm = 0;
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+        uint32_t d = (e >> k) + 1u + (uint32_t)k;
+        if ((int32_t)(v[k] - d) <= (int32_t)HALVE_AT) bm |= 1u << k;
+    }
+    bmask = __shfl_sync(0xffffffffu, bm, h);
+#pragma unroll
+    for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, nb[k], h);
+    return commit_epoch(s, w, c, B, h) ? 2 : 4;
+}
 
 __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
-    __shared__ uint4 sfine[2][GROUP];
+    __shared__ __align__(128) uint4 sfine[2][GROUP];
+    __shared__ __align__(128) uint4 sblk[2][32 * 4];
+    __shared__ __align__(8) uint64_t bars[2];
     const uint32_t lane = threadIdx.x;
+    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t phase0 = 0, phase1 = 0;   // parity of the next completion of each buffer's barrier
+
     for (;;) {
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(&a.counters[1], 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= a.counters[0]) break;
         const uint32_t pc = a.live[qi];
-        const uint32_t p = pc / NBIN, c = pc % NBIN;
+        const uint32_t p = pc / NBIN, cx = pc % NBIN;
         const uint32_t count = a.chain_count[pc];
         const uint32_t cbase = a.chain_base[pc];
         const uint32_t nblk = (count + 31u) >> 5;
         const size_t gbase = (size_t)p * a.cap + cbase;      // global element index of the chain start
         const size_t blk0 = gbase >> 5;                      // global 32-block index
-        const uint32_t ep0 = p * a.epcap + cbase / 8 + 16 * c;
-        const uint32_t ep_room = nblk * 4 + 16;              // records available to this chain
+        const uint32_t ep0 = p * a.epcap + cbase / 8 + 16 * cx;
+        WalkChain c;
+        c.rec = a.ep_rec + (size_t)ep0 * 2;
+        c.ep_room = nblk * 4 + 16;                           // records available to this chain
+        c.gbase32 = (uint32_t)gbase;
+        c.count = count;
+        c.lane = lane;
 
-        uint32_t base[NK];
-#pragma unroll
-        for (int k = 0; k < NK; k++)
-            base[k] = 0u - (a.blk_local[blk0 * 8 + k] + a.grp_pre[(blk0 >> 5) * 8 + k]);
-        if (lane < NK) a.ep_base[(size_t)ep0 * 8 + lane] = base[lane];
-        if (lane == NK) a.ep_start[ep0] = (uint32_t)gbase;
-        uint32_t nep = 1;
-        uint32_t cur = 0;  // chain-relative index of the first element of the current epoch
-        bool overflow = false;
+        auto prefetch = [&](uint32_t wb, uint32_t buf) {
+            if (lane == 0) {
+                const uint32_t nb = min(nblk - wb, 32u);
+                mbar_expect_tx(&bars[buf], nb * (32u * 16u + 64u));
+                bulk_g2s(&sfine[buf][0], a.fine + gbase + (size_t)wb * 32, nb * 32u * 16u, &bars[buf]);
+                bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + wb) * 4, nb * 64u, &bars[buf]);
+            }
+        };
+        prefetch(0, 0);
 
-        // prefetch window 0
+        WalkSt s;
         {
-            const uint4 *src = a.fine + gbase;
-            uint32_t nel = min(nblk * 32u, (uint32_t)GROUP);
-            for (uint32_t j = lane; j < nel; j += 32) cp_async16(&sfine[0][j], src + j);
-            cp_async_commit();
+            uint4 r0 = a.blk_rec4[blk0 * 4], r1 = a.blk_rec4[blk0 * 4 + 1];
+            s.base[0] = 0u - r0.x; s.base[1] = 0u - r0.y; s.base[2] = 0u - r0.z; s.base[3] = 0u - r0.w;
+            s.base[4] = 0u - r1.x; s.base[5] = 0u - r1.y;
         }
-        uint32_t wi = 0;
-        for (uint32_t wb = 0; wb < nblk; wb += 32, wi++) {
-            const uint32_t buf = wi & 1;
-            if (wb + 32 < nblk) {
-                const uint4 *src = a.fine + gbase + (size_t)(wb + 32) * 32;
-                uint32_t nel = min((nblk - (wb + 32)) * 32u, (uint32_t)GROUP);
-                for (uint32_t j = lane; j < nel; j += 32) cp_async16(&sfine[buf ^ 1][j], src + j);
-                cp_async_commit();
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncwarp();
+        if (lane == 0) {
+            c.rec[0] = make_uint4(s.base[0], s.base[1], s.base[2], s.base[3]);
+            c.rec[1] = make_uint4(s.base[4], s.base[5], c.gbase32, 0u);
+        }
+        s.nep = 1;
+        s.cur = 0;
+        s.overflow = false;
+        // Candidate binding counters (the ones that pass 1024 last): the two most recently seen.
+        uint32_t c1 = 5, c2 = 5;   // c1 = most recent; set from the first generic epoch
+        bool fast = false;
+        bool finished = false;
 
-            const uint32_t blk = wb + lane;
-            const bool valid = blk < nblk;
-            uint32_t cps[NK], cpe[NK];
+        uint32_t wi = 0;
+        for (uint32_t wb = 0; wb < nblk && !finished; wb += 32, wi++) {
+            const uint32_t buf = wi & 1;
+            if (wb + 32 < nblk) prefetch(wb + 32, buf ^ 1);
+            if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
+            WalkWin w;
+            w.sfine = &sfine[buf][0];
+            w.sblk = &sblk[buf][0];
+            w.wb = wb;
+            w.valid = wb + lane < nblk;
             {
-                size_t gb = blk0 + (valid ? blk : 0);
-                uint4 last = sfine[buf][(valid ? lane : 0) * 32 + 31];
-                uint32_t bt[NK] = {last.x & 0xffffu, last.x >> 16, last.y & 0xffffu, last.y >> 16, last.z & 0xffffu, last.z >> 16};
-#pragma unroll
-                for (int k = 0; k < NK; k++) {
-                    cps[k] = a.blk_local[gb * 8 + k] + a.grp_pre[(gb >> 5) * 8 + k];
-                    cpe[k] = cps[k] + bt[k];
-                }
+                uint4 r2 = sblk[buf][lane * 4 + 2], r3 = sblk[buf][lane * 4 + 3];
+                w.incl[0] = r2.x; w.incl[1] = r2.y; w.incl[2] = r2.z; w.incl[3] = r2.w; w.incl[4] = r3.x; w.incl[5] = r3.y;
             }
-            uint32_t my_epoch = nep - 1;  // epoch in effect at the start of my block
+            s.my_epoch = s.nep - 1;
+            s.curblk = (int)(s.cur >> 5) - (int)wb;
+            s.blkmask = s.curblk <= 0 ? 0xffffffffu : (s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk));
+            s.lanemask = 0xffffffffu << (s.cur & 31u);
             for (;;) {
-                // coarse: first block (at or after the one holding `cur`) at whose END every counter exceeds 1024
-                bool ok = valid;
-#pragma unroll
-                for (int k = 0; k < NK; k++) ok = ok && ((int32_t)(base[k] + cpe[k]) > (int32_t)HALVE_AT);
-                uint32_t m = __ballot_sync(0xffffffffu, ok);
-                int curblk = (int)(cur >> 5) - (int)wb;  // < 0: the epoch began in an earlier window
-                if (curblk >= 32) m = 0;
-                else if (curblk > 0) m &= ~((1u << curblk) - 1u);
-                if (!m) break;
-                const int B = __ffs(m) - 1;
-                // fine: first element of block B at which every counter exceeds 1024
-                uint4 f = sfine[buf][B * 32 + lane];
-                uint32_t U[NK] = {f.x & 0xffffu, f.x >> 16, f.y & 0xffffu, f.y >> 16, f.z & 0xffffu, f.z >> 16};
-                uint32_t T[NK], v[NK];
-                bool okf = true;
-#pragma unroll
-                for (int k = 0; k < NK; k++) {
-                    T[k] = __shfl_sync(0xffffffffu, cps[k], B) + U[k];  // prefix including this element
-                    v[k] = base[k] + T[k];
-                    okf = okf && ((int32_t)v[k] > (int32_t)HALVE_AT);
+                int r = 1;
+                if (fast) {
+                    // adjacent candidates are searched as a pair, otherwise only the most recent one
+                    const bool pair = (c1 > c2 ? c1 - c2 : c2 - c1) <= 1;
+                    const uint32_t ka = pair ? min(c1, c2) : c1, kb = pair ? max(c1, c2) : c1;
+                    switch (ka * 8 + kb) {
+                        case 0 * 8 + 0: r = fast_epochs<0, 0>(s, w, c); break;
+                        case 1 * 8 + 1: r = fast_epochs<1, 1>(s, w, c); break;
+                        case 2 * 8 + 2: r = fast_epochs<2, 2>(s, w, c); break;
+                        case 3 * 8 + 3: r = fast_epochs<3, 3>(s, w, c); break;
+                        case 4 * 8 + 4: r = fast_epochs<4, 4>(s, w, c); break;
+                        case 5 * 8 + 5: r = fast_epochs<5, 5>(s, w, c); break;
+                        case 0 * 8 + 1: r = fast_epochs<0, 1>(s, w, c); break;
+                        case 1 * 8 + 2: r = fast_epochs<1, 2>(s, w, c); break;
+                        case 2 * 8 + 3: r = fast_epochs<2, 3>(s, w, c); break;
+                        case 3 * 8 + 4: r = fast_epochs<3, 4>(s, w, c); break;
+                        case 4 * 8 + 5: r = fast_epochs<4, 5>(s, w, c); break;
+                        default: r = 1; break;
+                    }
+                    if (r == 0) break;
+                    if (r == 2) { finished = true; break; }
                 }
-                uint32_t fm = __ballot_sync(0xffffffffu, okf);
-                if (B == curblk) fm &= ~((1u << (cur & 31u)) - 1u);
-                if (fm == 0) { overflow = true; atomicOr(&a.counters[2], 2u); break; }  // cannot happen: the block's last element satisfies the test
-                const int h = __ffs(fm) - 1;
-#pragma unroll
-                for (int k = 0; k < NK; k++) {
-                    uint32_t s = __shfl_sync(0xffffffffu, v[k], h) >> 1;   // parameter_selection.rs:58-63
-                    uint32_t th = __shfl_sync(0xffffffffu, T[k], h);
-                    base[k] = s - th;
-                }
-                cur = (wb + (uint32_t)B) * 32u + (uint32_t)h + 1u;
-                if (nep + 1 < ep_room) {
-                    if (lane < NK) a.ep_base[(size_t)(ep0 + nep) * 8 + lane] = base[lane];
-                    if (lane == NK) a.ep_start[ep0 + nep] = (uint32_t)(gbase + cur);
-                } else {
-                    overflow = true;
-                }
-                nep++;
-                if ((int)lane > B) my_epoch++;
-                if (cur >= count) break;
+                // one epoch on all six counters, then refresh the candidates
+                uint32_t bmask = 0;
+                r = generic_epoch(s, w, c, bmask);
+                if (r == 0) break;
+                if (r == 3) { s.overflow = true; atomicOr(&a.counters[2], 2u); finished = true; break; }
+                const uint32_t hi = 31 - __clz(bmask), lo = __ffs(bmask) - 1;
+                if (hi != lo) { c1 = hi; c2 = lo; }
+                else if (!fast) { c1 = hi; c2 = hi; }          // first epoch of the chain
+                else if (hi != c1) { c2 = c1; c1 = hi; }
+                fast = true;
+                if (r == 2) { finished = true; break; }
             }
-            if (valid) a.blk_epoch[blk0 + blk] = ep0 + my_epoch;
+            if (w.valid) a.blk_epoch[blk0 + wb + lane] = ep0 + s.my_epoch;
             __syncwarp();
         }
         if (lane == 0) {
-            if (overflow) atomicOr(&a.counters[2], 1u);
-            else a.ep_start[ep0 + nep] = 0xFFFFFFFFu;  // sentinel
+            if (s.overflow) atomicOr(&a.counters[2], 1u);
+            else c.rec[2 * s.nep + 1] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // sentinel
         }
     }
 }
 
 // kfill: one thread per grouped element.
-__global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, const uint32_t *__restrict__ blk_local,
-                                               const uint32_t *__restrict__ grp_pre, const uint32_t *__restrict__ blk_epoch,
-                                               const uint32_t *__restrict__ ep_start, const uint32_t *__restrict__ ep_base,
+__global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, const uint4 *__restrict__ blk_rec4,
+                                               const uint32_t *__restrict__ blk_epoch, const uint4 *__restrict__ ep_rec,
                                                const uint32_t *__restrict__ plane_used, uint32_t cap, uint32_t np,
                                                uint8_t *__restrict__ k_grp) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -486,14 +672,25 @@ __global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, c
     if (f.w == PAD_E) return;
     size_t blk = g >> 5;
     uint32_t ep = blk_epoch[blk];
-    while (ep_start[ep + 1] <= (uint32_t)g) ep++;
+    uint4 b1 = ep_rec[(size_t)ep * 2 + 1];
+    for (;;) {
+        uint4 n1 = ep_rec[(size_t)ep * 2 + 3];
+        if (n1.z > (uint32_t)g) break;
+        ep++;
+        b1 = n1;
+    }
+    const uint4 b0 = ep_rec[(size_t)ep * 2];
     uint32_t e = f.w;
-    uint32_t U[NK] = {f.x & 0xffffu, f.x >> 16, f.y & 0xffffu, f.y >> 16, f.z & 0xffffu, f.z >> 16};
+    uint32_t U[NK];
+    unpack6(f, U);
+    const uint4 e0 = blk_rec4[blk * 4], e1 = blk_rec4[blk * 4 + 1];
+    const uint32_t cps[NK] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y};
+    const uint32_t eb[NK] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y};
     uint32_t v[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) {
         uint32_t d = (e >> k) + 1u + (uint32_t)k;
-        v[k] = ep_base[(size_t)ep * 8 + k] + blk_local[blk * 8 + k] + grp_pre[(blk >> 5) * 8 + k] + U[k] - d;
+        v[k] = eb[k] + cps[k] + U[k] - d;   // counters before this element's update
     }
     k_grp[g] = (uint8_t)argmin_last(v);
 }
@@ -782,7 +979,7 @@ struct Layout {
     uint16_t *e_grp;
     uint32_t *gidx;
     uint4 *fine;
-    uint32_t *blk_local, *grp_tot, *ep_start, *ep_base, *blk_epoch;
+    uint32_t *blk_rec, *grp_tot, *super_tot, *ep_rec, *blk_epoch;
     uint8_t *k_grp;
     uint32_t *rec, *tile_bits;
     uint64_t *tile_off, *plane_bits, *img_off;
@@ -808,10 +1005,10 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
     L.e_grp = c.take<uint16_t>(np * g.cap);
     L.gidx = c.take<uint32_t>(np * g.npix + 8);
     L.fine = c.take<uint4>(np * g.cap);
-    L.blk_local = c.take<uint32_t>(np * (g.cap / 32) * 8);
+    L.blk_rec = c.take<uint32_t>(np * (g.cap / 32) * BLK_REC);
     L.grp_tot = c.take<uint32_t>(np * g.gpp * 8 + 8);
-    L.ep_start = c.take<uint32_t>(np * g.epcap + 8);
-    L.ep_base = c.take<uint32_t>((np * g.epcap + 8) * 8);
+    L.super_tot = c.take<uint32_t>((np * g.gpp / 1024 + 2) * 8);
+    L.ep_rec = c.take<uint32_t>((np * g.epcap + 8) * 8);
     L.blk_epoch = c.take<uint32_t>(np * (g.cap / 32));
     L.k_grp = c.take<uint8_t>(np * g.cap);
     L.rec = c.take<uint32_t>(np * g.npix + 8);
@@ -912,29 +1109,33 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_PREFIX);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.grp_tot, 0, ((size_t)ngroups * 8 + 8) * sizeof(uint32_t), st));
-                k_prefix<<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_local, L.grp_tot);
+                k_prefix<<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
                 s.launched();
             }
             {
                 StageScope s(ctx, ST_GRPSCAN);
-                k_grpscan<<<1, 1024, 0, st>>>(L.grp_tot, ngroups);
-                s.launched();
+                const unsigned nsuper = (ngroups + 1023) / 1024;
+                k_grpscan1<<<nsuper, 1024, 0, st>>>(L.grp_tot, ngroups, L.super_tot);
+                k_grpscan2<<<1, 1024, 0, st>>>(L.super_tot, nsuper);
+                const size_t nquarters = (size_t)ngroups * 32 * 4;
+                k_blkfinal<<<(unsigned)((nquarters + 255) / 256), 256, 0, st>>>((uint4 *)L.blk_rec, L.grp_tot, L.super_tot, L.plane_used, g.gpp, nquarters);
+                s.launched(3);
             }
             {
                 StageScope s(ctx, ST_WALK);
                 WalkArgs wa;
-                wa.fine = L.fine; wa.blk_local = L.blk_local; wa.grp_pre = L.grp_tot;
+                wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
-                wa.counters = L.counters; wa.ep_start = L.ep_start; wa.ep_base = L.ep_base; wa.blk_epoch = L.blk_epoch;
+                wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
                 wa.cap = g.cap; wa.epcap = g.epcap;
-                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 7);
+                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 6);
                 k_walk<<<blocks, 32, 0, st>>>(wa);
                 s.launched();
             }
             {
                 StageScope s(ctx, ST_KFILL);
                 size_t total = np * (size_t)g.cap;
-                k_kfill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L.fine, L.blk_local, L.grp_tot, L.blk_epoch, L.ep_start, L.ep_base,
+                k_kfill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L.fine, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec,
                                                                          L.plane_used, g.cap, (uint32_t)np, L.k_grp);
                 s.launched();
             }
