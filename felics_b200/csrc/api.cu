@@ -306,5 +306,12 @@ int felics_debug_last_records(felics_ctx *ctx, uint32_t *out, size_t count) {
     return FELICS_OK;
 }
 
+// Debug aid: the 8 device counters of the last encode sub-batch (queue sizes, flags, walker cycle counts).
+int felics_debug_counters(felics_ctx *ctx, uint32_t *out8) {
+    if (!ctx || !out8) return FELICS_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < 8; i++) out8[i] = ctx->dbg_counters[i];
+    return FELICS_OK;
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

@@ -59,6 +59,7 @@ struct felics_ctx {
     // debug: device pointer / count of the per-pixel code records of the last encode
     const uint32_t *dbg_rec = nullptr;
     size_t dbg_rec_count = 0;
+    uint32_t dbg_counters[8] = {0};
 };
 
 namespace felics {

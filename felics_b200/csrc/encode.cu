@@ -484,27 +484,54 @@ __device__ __forceinline__ int32_t element_state(const WalkSt &s, const WalkWin 
     return mn;
 }
 
-// Fast path: the block is chosen by looking at the candidate counters KA, KB only (fixed registers);
-// the element test then uses all six counters, which both finds the halving element and proves
-// that no other counter is slower.  Returns 0: no halving left in this window, 1: needs the generic
-// path (another counter passes 1024 later than the candidates), 2: chain finished.
-template <int KA, int KB>
-__device__ __forceinline__ int fast_epochs(WalkSt &s, const WalkWin &w, const WalkChain &c) {
+// Fast path on the candidate counters ka, kb (runtime indices; shared memory is addressed
+// dynamically so no register selects are needed).  Counter k lives in lane k (`mybase`); the
+// candidates' bases are also kept warp-uniform in ba/bb.  Block and element are found by looking
+// at the candidates only; then lanes 0..5 each update their own counter at the element found and
+// a vote proves that every counter is above 1024 there (i.e. no other counter is slower).
+// Returns 0: no halving left in this window, 1: needs the generic path, 2: chain finished.
+struct FastSt {
+    uint32_t mybase;      // base of counter (lane & 7), meaningful in lanes 0..5
+    uint32_t ba, bb;      // base[ka], base[kb] (uniform)
+    uint32_t ia, ib;      // cost prefix at the end of MY block for ka, kb
+};
+__device__ __forceinline__ int fast_epochs(WalkSt &s, FastSt &f, const WalkWin &w, const WalkChain &c, uint32_t ka, uint32_t kb) {
+    const uint32_t *sblk32 = reinterpret_cast<const uint32_t *>(w.sblk);
+    const uint16_t *sfine16 = reinterpret_cast<const uint16_t *>(w.sfine);
+    const uint32_t lk = c.lane & 7u;
+    uint32_t *rec32 = reinterpret_cast<uint32_t *>(c.rec);
     for (;;) {
-        bool ok = w.valid && ((int32_t)(s.base[KA] + w.incl[KA]) > (int32_t)HALVE_AT);
-        if (KA != KB) ok = ok && ((int32_t)(s.base[KB] + w.incl[KB]) > (int32_t)HALVE_AT);
+        bool ok = w.valid && ((int32_t)(f.ba + f.ia) > (int32_t)HALVE_AT) && ((int32_t)(f.bb + f.ib) > (int32_t)HALVE_AT);
         const uint32_t m = __ballot_sync(0xffffffffu, ok) & s.blkmask;
         if (!m) return 0;
         const int B = __ffs(m) - 1;
-        uint32_t nb[NK], v[NK], e;
-        const int32_t mn = element_state(s, w, B, c.lane, nb, v, e);
-        uint32_t fm = __ballot_sync(0xffffffffu, mn > (int32_t)HALVE_AT);
+        const uint32_t ta = f.ba + sblk32[B * 16 + ka], tb = f.bb + sblk32[B * 16 + kb];
+        const uint32_t ua = sfine16[(B * 32 + c.lane) * 8 + ka], ub = sfine16[(B * 32 + c.lane) * 8 + kb];
+        const bool okf = ((int32_t)(ta + ua) > (int32_t)HALVE_AT) && ((int32_t)(tb + ub) > (int32_t)HALVE_AT);
+        uint32_t fm = __ballot_sync(0xffffffffu, okf);
         if (B == s.curblk) fm &= s.lanemask;
-        if (!fm) return 1;
+        if (!fm) return 1;   // cannot happen (the block's last element passes); be safe
         const int h = __ffs(fm) - 1;
-#pragma unroll
-        for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, nb[k], h);
-        if (commit_epoch(s, w, c, B, h)) return 2;
+        // lane k: counter k after the update of element (B, h)
+        const uint32_t T = sblk32[B * 16 + lk] + sfine16[(B * 32 + h) * 8 + lk];
+        const uint32_t v = f.mybase + T;
+        if (!__all_sync(0xffffffffu, ((int32_t)v > (int32_t)HALVE_AT) || c.lane >= NK)) return 1;   // another counter is slower
+        f.mybase = (v >> 1) - T;                       // parameter_selection.rs:58-63, re-based
+        f.ba = __shfl_sync(0xffffffffu, f.mybase, ka);
+        f.bb = __shfl_sync(0xffffffffu, f.mybase, kb);
+        // commit
+        s.cur = (w.wb + (uint32_t)B) * 32u + (uint32_t)h + 1u;
+        s.curblk = B + (h == 31 ? 1 : 0);
+        s.blkmask = s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk);
+        s.lanemask = 0xffffffffu << ((uint32_t)(h + 1) & 31u);
+        if (s.nep + 1 < c.ep_room) {
+            if (c.lane < 8) rec32[s.nep * 8 + c.lane] = c.lane < NK ? f.mybase : (c.lane == NK ? c.gbase32 + s.cur : 0u);
+        } else {
+            s.overflow = true;
+        }
+        s.nep++;
+        if ((int)c.lane > B) s.my_epoch++;
+        if (s.cur >= c.count) return 2;
     }
 }
 
@@ -619,20 +646,13 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                     // adjacent candidates are searched as a pair, otherwise only the most recent one
                     const bool pair = (c1 > c2 ? c1 - c2 : c2 - c1) <= 1;
                     const uint32_t ka = pair ? min(c1, c2) : c1, kb = pair ? max(c1, c2) : c1;
-                    switch (ka * 8 + kb) {
-                        case 0 * 8 + 0: r = fast_epochs<0, 0>(s, w, c); break;
-                        case 1 * 8 + 1: r = fast_epochs<1, 1>(s, w, c); break;
-                        case 2 * 8 + 2: r = fast_epochs<2, 2>(s, w, c); break;
-                        case 3 * 8 + 3: r = fast_epochs<3, 3>(s, w, c); break;
-                        case 4 * 8 + 4: r = fast_epochs<4, 4>(s, w, c); break;
-                        case 5 * 8 + 5: r = fast_epochs<5, 5>(s, w, c); break;
-                        case 0 * 8 + 1: r = fast_epochs<0, 1>(s, w, c); break;
-                        case 1 * 8 + 2: r = fast_epochs<1, 2>(s, w, c); break;
-                        case 2 * 8 + 3: r = fast_epochs<2, 3>(s, w, c); break;
-                        case 3 * 8 + 4: r = fast_epochs<3, 4>(s, w, c); break;
-                        case 4 * 8 + 5: r = fast_epochs<4, 5>(s, w, c); break;
-                        default: r = 1; break;
-                    }
+                    FastSt f;
+                    f.mybase = sel6(s.base, lane & 7u);
+                    f.ba = sel6(s.base, ka); f.bb = sel6(s.base, kb);
+                    f.ia = sel6(w.incl, ka); f.ib = sel6(w.incl, kb);
+                    r = fast_epochs(s, f, w, c, ka, kb);
+#pragma unroll
+                    for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, f.mybase, k);
                     if (r == 0) break;
                     if (r == 2) { finished = true; break; }
                 }
@@ -1166,6 +1186,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
         FELICS_CUDA_TRY(cudaMemcpyAsync(h_off, L.img_off, (ni + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
         FELICS_CUDA_TRY(cudaMemcpyAsync(h_cnt, L.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int i = 0; i < 8; i++) ctx->dbg_counters[i] = h_cnt[i];
         if (h_cnt[2]) {
             set_error("internal: epoch record capacity exceeded (flags %u)", h_cnt[2]);
             return FELICS_ERR_CUDA;

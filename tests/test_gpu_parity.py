@@ -197,3 +197,13 @@ def test_module_level_api(golden_images):  # compress_image / decompress_image (
     felics_b200.compress_image(sink, img)
     assert sink.getvalue() == fo.compress(img)
     assert np.array_equal(felics_b200.decompress_image(io.BytesIO(sink.getvalue())), img)
+
+
+def test_long_chains(codec):
+    # chains longer than 65,536 elements take the table-driven walker (k_walk_long)
+    check(codec, gnat_image(2048, 1024))                                           # stationary: one binding counter
+    rng = np.random.default_rng(21)
+    check(codec, rng.integers(0, 256, (600, 700), dtype=np.uint8).repeat(2, axis=1))  # noise, wide cost ranges
+    yy, xx = np.mgrid[0:900, 0:1400]
+    check(codec, np.clip(90 + ((xx * 3 + yy) // 11) % 60 + rng.integers(-1, 2, xx.shape), 0, 255).astype(np.uint8))
+    check(codec, np.clip(128 + rng.normal(0, 1.2, (1100, 1000)), 0, 255).astype(np.uint8))  # near-tied counters
