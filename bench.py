@@ -315,19 +315,13 @@ def run_ours(args):
     dec_stage = codec.stage_times()
     codec.profile(False)
 
+    from felics_b200 import sharding
+
     def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.reduce_scalar(x, "max", device=dev)
 
     def reduce_sum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return sharding.reduce_scalar(x, "sum", device=dev)
 
     tot_dev_ms = reduce_max(sum(ms_dev))
     tot_e2e_ms = reduce_max(sum(ms_e2e))
