@@ -118,6 +118,7 @@ def load_library() -> C.CDLL:
     L.felics_profile_total_launches.argtypes = [vp]
     L.felics_profile_total_launches.restype = C.c_uint64
     L.felics_debug_last_records.argtypes = [vp, vp, sz]
+    L.felics_debug_counters.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -324,6 +325,13 @@ class Codec:
 
     def total_launches(self) -> int:
         return int(self._lib.felics_profile_total_launches(self._h))
+
+    def debug_counters(self) -> np.ndarray:
+        """Device counters of the last encode: [0] live chains, [2] error flags, [3] chains tried by the
+        speculative walk, [4] chains it resolved."""
+        out = np.zeros(8, dtype=np.uint32)
+        self._lib.felics_debug_counters(self._h, out.ctypes.data)
+        return out
 
     def debug_last_records(self, count: int) -> np.ndarray:
         out = np.zeros(count, dtype=np.uint32)

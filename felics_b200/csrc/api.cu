@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 namespace felics {
@@ -73,7 +74,7 @@ int profile_collect(felics_ctx *ctx) {
 }
 
 static const char *kStageNames[ST_COUNT] = {"planes", "hist", "chainscan", "tilebase", "scatter", "prefix", "grpscan",
-                                            "walk", "kfill", "code", "bitscan", "pack", "decode", "unplane"};
+                                            "spec", "walk", "kfill", "code", "bitscan", "pack", "decode", "unplane"};
 
 static int check_header(const felics_header *hdr) {
     if (!hdr) { set_error("null header"); return FELICS_ERR_INVALID_ARGUMENT; }
@@ -107,6 +108,10 @@ int felics_ctx_create(int device, felics_ctx **out) {
     felics_ctx *ctx = new (std::nothrow) felics_ctx();
     if (!ctx) return FELICS_ERR_CUDA;
     ctx->device = device;
+    {
+        const char *ns = getenv("FELICS_B200_NO_SPEC");   // debug switch: force the serial epoch walk
+        ctx->no_spec = ns && ns[0] == '1';
+    }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return FELICS_ERR_CUDA; }
     ctx->stream = ctx->own_stream;

@@ -19,6 +19,7 @@ enum Stage : int {
     ST_SCATTER,      // stable grouping of residuals by context
     ST_PREFIX,       // per-32-block code-cost prefix sums for the 6 k candidates
     ST_GRPSCAN,      // scan of the per-1024 group totals
+    ST_SPEC,         // speculative parallel epoch walk of long chains (verified; falls back to ST_WALK)
     ST_WALK,         // halving-epoch walk (the sequential part of the estimator)
     ST_KFILL,        // k per out-of-range pixel
     ST_CODE,         // code word + length per pixel, bits per tile
@@ -50,6 +51,7 @@ struct felics_ctx {
     size_t pinned_cap = 0;
 
     bool prof = false;
+    bool no_spec = false;         // debug/bench switch: skip the speculative walk
     std::vector<felics::ProfEntry> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     double stage_ms[felics::ST_COUNT] = {0};

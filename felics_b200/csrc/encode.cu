@@ -22,6 +22,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include "sp_walk.cuh"
+
 namespace felics {
 
 // ------------------------------------------------------------------------------------
@@ -386,6 +388,7 @@ struct WalkArgs {
     uint32_t *blk_epoch;    // epoch in effect at the start of each 32-block
     uint32_t cap;           // grouped elements per plane
     uint32_t epcap;         // epoch records per plane
+    const uint8_t *resolved; // per (plane, context): 1 = already resolved by the speculative walk (may be null)
 };
 
 // register-array element by a runtime index without forcing the array into local memory
@@ -579,6 +582,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= a.counters[0]) break;
         const uint32_t pc = a.live[qi];
+        if (a.resolved && a.resolved[pc]) continue;
         const uint32_t p = pc / NBIN, cx = pc % NBIN;
         const uint32_t count = a.chain_count[pc];
         const uint32_t cbase = a.chain_base[pc];
@@ -1003,6 +1007,13 @@ struct Layout {
     uint8_t *k_grp;
     uint32_t *rec, *tile_bits;
     uint64_t *tile_off, *plane_bits, *img_off;
+    // speculative walk (single big images only; null otherwise)
+    bool sp;
+    SpSizes spsz;
+    SpDesc *sp_desc;
+    uint32_t *sp_seg_desc, *sp_grp_desc, *sp_eb_desc, *sp_counts, *sp_map, *sp_pre, *sp_gmap, *sp_grp_xin, *sp_grp_nbefore, *sp_chain_n, *sp_chain_fail, *sp_sblk;
+    unsigned long long *sp_ablk;
+    uint8_t *sp_resolved;
     size_t bytes;
 };
 
@@ -1036,6 +1047,26 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
     L.tile_off = c.take<uint64_t>(np * g.tpp + 8);
     L.plane_bits = c.take<uint64_t>(np + 8);
     L.img_off = c.take<uint64_t>(ni + 8);
+    L.sp = np <= (size_t)SP_MAX_PLANES && g.npix >= SP_MIN_COUNT;
+    if (L.sp) {
+        const SpSizes z = sp_sizes((uint32_t)np, g.cap);
+        L.spsz = z;
+        L.sp_desc = c.take<SpDesc>(z.max_desc);
+        L.sp_seg_desc = c.take<uint32_t>(z.max_seg);
+        L.sp_grp_desc = c.take<uint32_t>(z.max_grp);
+        L.sp_eb_desc = c.take<uint32_t>(z.max_eb);
+        L.sp_counts = c.take<uint32_t>(8);
+        L.sp_map = c.take<uint32_t>((size_t)z.max_seg * SP_DOM);
+        L.sp_pre = c.take<uint32_t>((size_t)z.max_seg * SP_DOM);
+        L.sp_gmap = c.take<uint32_t>((size_t)z.max_grp * SP_DOM);
+        L.sp_grp_xin = c.take<uint32_t>(z.max_grp);
+        L.sp_grp_nbefore = c.take<uint32_t>(z.max_grp);
+        L.sp_chain_n = c.take<uint32_t>(z.max_desc);
+        L.sp_chain_fail = c.take<uint32_t>(z.max_desc);
+        L.sp_sblk = c.take<uint32_t>((size_t)z.max_eb * 8);
+        L.sp_ablk = c.take<unsigned long long>((size_t)z.max_eb * 8);
+        L.sp_resolved = c.take<uint8_t>(np * NBIN);
+    }
     L.bytes = align_up(c.off, 256);
     return L;
 }
@@ -1141,9 +1172,40 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_blkfinal<<<(unsigned)((nquarters + 255) / 256), 256, 0, st>>>((uint4 *)L.blk_rec, L.grp_tot, L.super_tot, L.plane_used, g.gpp, nquarters);
                 s.launched(3);
             }
+            const uint8_t *resolved = nullptr;
+            if (L.sp && !ctx->no_spec) {
+                StageScope s(ctx, ST_SPEC);
+                SpArgs sa;
+                sa.chain_count = L.chain_count; sa.chain_base = L.chain_base; sa.fine = L.fine; sa.blk_rec4 = (const uint4 *)L.blk_rec;
+                sa.desc = L.sp_desc; sa.seg_desc = L.sp_seg_desc; sa.grp_desc = L.sp_grp_desc; sa.eb_desc = L.sp_eb_desc; sa.counts = L.sp_counts;
+                sa.map = L.sp_map; sa.pre = L.sp_pre; sa.gmap = L.sp_gmap; sa.grp_xin = L.sp_grp_xin; sa.grp_nbefore = L.sp_grp_nbefore;
+                sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.sblk = L.sp_sblk;
+                sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch; sa.resolved = L.sp_resolved; sa.dbg = L.counters;
+                sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz;
+                static bool attr_done = false;
+                if (!attr_done) {
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
+                    attr_done = true;
+                }
+                FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_resolved, 0, np * NBIN, st));
+                const SpSizes &z = L.spsz;
+                k_sp_plan<<<1, NBIN, 0, st>>>(sa);
+                k_sp_maps<<<z.max_seg, 1024, sizeof(SpSegSmem), st>>>(sa);
+                k_sp_compose<<<z.max_grp, 1024, 0, st>>>(sa);
+                k_sp_scan<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
+                k_sp_emit<<<z.max_seg, 256, sizeof(SpSegSmem), st>>>(sa);
+                k_sp_blocksum<<<z.max_eb, 32, 0, st>>>(sa);
+                k_sp_blockscan<<<z.max_desc, 32, 0, st>>>(sa);
+                k_sp_finish<<<z.max_eb, 32, 0, st>>>(sa);
+                k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
+                s.launched(9);
+                resolved = L.sp_resolved;
+            }
             {
                 StageScope s(ctx, ST_WALK);
                 WalkArgs wa;
+                wa.resolved = resolved;
                 wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
