@@ -54,6 +54,11 @@ StageScope::StageScope(felics_ctx *c, int st) : ctx(c), stage(st) {
     cudaEventRecord(a, ctx->stream);
 }
 StageScope::~StageScope() {
+    static const bool sync_each = getenv("FELICS_B200_SYNC") != nullptr;   // debug: localise a faulting stage
+    if (sync_each) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) fprintf(stderr, "felics_b200: stage %d failed: %s\n", stage, cudaGetErrorString(e));
+    }
     if (!a) return;
     cudaEventRecord(b, ctx->stream);
     ctx->prof_pending.push_back({stage, a, b});

@@ -391,12 +391,6 @@ struct WalkArgs {
     const uint8_t *resolved; // per (plane, context): 1 = already resolved by the speculative walk (may be null)
 };
 
-// register-array element by a runtime index without forcing the array into local memory
-__device__ __forceinline__ uint32_t sel6(const uint32_t v[NK], uint32_t i) {
-    uint32_t r = v[0];
-    r = i == 1 ? v[1] : r; r = i == 2 ? v[2] : r; r = i == 3 ? v[3] : r; r = i == 4 ? v[4] : r; r = i == 5 ? v[5] : r;
-    return r;
-}
 __device__ __forceinline__ void unpack6(const uint4 &f, uint32_t U[NK]) {
     U[0] = f.x & 0xffffu; U[1] = f.x >> 16; U[2] = f.y & 0xffffu; U[3] = f.y >> 16; U[4] = f.z & 0xffffu; U[5] = f.z >> 16;
 }
@@ -424,157 +418,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!done);
 }
 
-// ---- epoch walk building blocks ------------------------------------------------------------------
-struct WalkWin {             // constants of the current window (32 blocks = 1024 elements)
-    const uint4 *sfine;      // shared: fine records of the window
-    const uint4 *sblk;       // shared: block records of the window (4 x uint4 per block)
-    uint32_t wb;             // first block of the window (chain-relative)
-    bool valid;              // my block exists
-    uint32_t incl[NK];       // cost prefix at the END of my block
+// ---- epoch walk: one warp per chain ---------------------------------------------------------------
+// The six counters are replicated in every lane (base[k], re-based: counter before element t =
+// base[k] + T_k(t)).  Windows of 32 blocks x 32 elements arrive by TMA, WALK_BUF in flight.  Per epoch:
+//   block level    lane l holds the prefixes at the END of block l; the first block (at or after the
+//                  current one) where all six counters have passed 1024 holds the halving element
+//   element level  lane l looks at element l of that block; the first element where all six counters
+//                  have passed 1024 is the halving (parameter_selection.rs:58), every lane has already
+//                  computed the re-based halved counters for its own element, the winner's are shuffled out
+// No assumption about which counter binds, so the walk is exact for any data.
+constexpr int WALK_BUF = 4;
+struct WalkSmem {
+    uint4 fine[WALK_BUF][GROUP];
+    uint4 blk[WALK_BUF][32 * 4];
+    uint64_t bars[WALK_BUF];
 };
-struct WalkSt {              // state of the walk along one chain
-    uint32_t base[NK];       // counters before element t are base + T(t)
-    uint32_t cur;            // chain-relative first element of the current epoch
-    int curblk;              // block (window-relative) holding `cur`; <= 0 when at/before the window start
-    uint32_t blkmask;        // lanes (= blocks) at or after curblk
-    uint32_t lanemask;       // lanes (= elements) at or after `cur` inside curblk
-    uint32_t nep;            // epochs recorded so far
-    uint32_t my_epoch;       // epoch in effect at the start of my block
-    bool overflow;
-};
-struct WalkChain {
-    uint4 *rec;
-    uint32_t ep_room, gbase32, count, lane;
-};
-
-// a halving happened at element h of block B: record the new epoch
-__device__ __forceinline__ bool commit_epoch(WalkSt &s, const WalkWin &w, const WalkChain &c, int B, int h) {
-    s.cur = (w.wb + (uint32_t)B) * 32u + (uint32_t)h + 1u;
-    s.curblk = B + (h == 31 ? 1 : 0);
-    s.blkmask = s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk);
-    s.lanemask = 0xffffffffu << ((uint32_t)(h + 1) & 31u);
-    if (s.nep + 1 < c.ep_room) {
-        if (c.lane == 0) {
-            c.rec[2 * s.nep] = make_uint4(s.base[0], s.base[1], s.base[2], s.base[3]);
-            c.rec[2 * s.nep + 1] = make_uint4(s.base[4], s.base[5], c.gbase32 + s.cur, 0u);
-        }
-    } else {
-        s.overflow = true;
-    }
-    s.nep++;
-    if ((int)c.lane > B) s.my_epoch++;
-    return s.cur >= c.count;
-}
-
-// per-lane: all six counters after MY element of block B, their minimum, and the base the next
-// epoch would have if the halving fell on my element (parameter_selection.rs:58-63, re-based)
-__device__ __forceinline__ int32_t element_state(const WalkSt &s, const WalkWin &w, int B, uint32_t lane, uint32_t nb[NK],
-                                                 uint32_t v[NK], uint32_t &e_out) {
-    const uint4 f = w.sfine[B * 32 + lane];
-    const uint4 e0 = w.sblk[B * 4], e1 = w.sblk[B * 4 + 1];
-    const uint32_t cps[NK] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y};
-    uint32_t U[NK];
-    unpack6(f, U);
-    e_out = f.w;
-    int32_t mn = 0x7fffffff;
-#pragma unroll
-    for (int k = 0; k < NK; k++) {
-        uint32_t T = cps[k] + U[k];      // cost prefix including my element
-        v[k] = s.base[k] + T;            // counter after my element's update
-        mn = min(mn, (int32_t)v[k]);
-        nb[k] = (v[k] >> 1) - T;
-    }
-    return mn;
-}
-
-// Fast path on the candidate counters ka, kb (runtime indices; shared memory is addressed
-// dynamically so no register selects are needed).  Counter k lives in lane k (`mybase`); the
-// candidates' bases are also kept warp-uniform in ba/bb.  Block and element are found by looking
-// at the candidates only; then lanes 0..5 each update their own counter at the element found and
-// a vote proves that every counter is above 1024 there (i.e. no other counter is slower).
-// Returns 0: no halving left in this window, 1: needs the generic path, 2: chain finished.
-struct FastSt {
-    uint32_t mybase;      // base of counter (lane & 7), meaningful in lanes 0..5
-    uint32_t ba, bb;      // base[ka], base[kb] (uniform)
-    uint32_t ia, ib;      // cost prefix at the end of MY block for ka, kb
-};
-__device__ __forceinline__ int fast_epochs(WalkSt &s, FastSt &f, const WalkWin &w, const WalkChain &c, uint32_t ka, uint32_t kb) {
-    const uint32_t *sblk32 = reinterpret_cast<const uint32_t *>(w.sblk);
-    const uint16_t *sfine16 = reinterpret_cast<const uint16_t *>(w.sfine);
-    const uint32_t lk = c.lane & 7u;
-    uint32_t *rec32 = reinterpret_cast<uint32_t *>(c.rec);
-    for (;;) {
-        bool ok = w.valid && ((int32_t)(f.ba + f.ia) > (int32_t)HALVE_AT) && ((int32_t)(f.bb + f.ib) > (int32_t)HALVE_AT);
-        const uint32_t m = __ballot_sync(0xffffffffu, ok) & s.blkmask;
-        if (!m) return 0;
-        const int B = __ffs(m) - 1;
-        const uint32_t ta = f.ba + sblk32[B * 16 + ka], tb = f.bb + sblk32[B * 16 + kb];
-        const uint32_t ua = sfine16[(B * 32 + c.lane) * 8 + ka], ub = sfine16[(B * 32 + c.lane) * 8 + kb];
-        const bool okf = ((int32_t)(ta + ua) > (int32_t)HALVE_AT) && ((int32_t)(tb + ub) > (int32_t)HALVE_AT);
-        uint32_t fm = __ballot_sync(0xffffffffu, okf);
-        if (B == s.curblk) fm &= s.lanemask;
-        if (!fm) return 1;   // cannot happen (the block's last element passes); be safe
-        const int h = __ffs(fm) - 1;
-        // lane k: counter k after the update of element (B, h)
-        const uint32_t T = sblk32[B * 16 + lk] + sfine16[(B * 32 + h) * 8 + lk];
-        const uint32_t v = f.mybase + T;
-        if (!__all_sync(0xffffffffu, ((int32_t)v > (int32_t)HALVE_AT) || c.lane >= NK)) return 1;   // another counter is slower
-        f.mybase = (v >> 1) - T;                       // parameter_selection.rs:58-63, re-based
-        f.ba = __shfl_sync(0xffffffffu, f.mybase, ka);
-        f.bb = __shfl_sync(0xffffffffu, f.mybase, kb);
-        // commit
-        s.cur = (w.wb + (uint32_t)B) * 32u + (uint32_t)h + 1u;
-        s.curblk = B + (h == 31 ? 1 : 0);
-        s.blkmask = s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk);
-        s.lanemask = 0xffffffffu << ((uint32_t)(h + 1) & 31u);
-        if (s.nep + 1 < c.ep_room) {
-            if (c.lane < 8) rec32[s.nep * 8 + c.lane] = c.lane < NK ? f.mybase : (c.lane == NK ? c.gbase32 + s.cur : 0u);
-        } else {
-            s.overflow = true;
-        }
-        s.nep++;
-        if ((int)c.lane > B) s.my_epoch++;
-        if (s.cur >= c.count) return 2;
-    }
-}
-
-// One epoch on all six counters.  Returns 0: no halving left in this window, 2: chain finished,
-// 3: internal error, 4: epoch done (bmask = the counters that passed 1024 last).
-__device__ __forceinline__ int generic_epoch(WalkSt &s, const WalkWin &w, const WalkChain &c, uint32_t &bmask) {
-    bool ok = w.valid;
-#pragma unroll
-    for (int k = 0; k < NK; k++) ok = ok && ((int32_t)(s.base[k] + w.incl[k]) > (int32_t)HALVE_AT);
-    const uint32_t m = __ballot_sync(0xffffffffu, ok) & s.blkmask;
-    if (!m) return 0;
-    const int B = __ffs(m) - 1;
-    uint32_t nb[NK], v[NK], e;
-    const int32_t mn = element_state(s, w, B, c.lane, nb, v, e);
-    uint32_t fm = __ballot_sync(0xffffffffu, mn > (int32_t)HALVE_AT);
-    if (B == s.curblk) fm &= s.lanemask;
-    if (!fm) return 3;   // cannot happen: the block's last element passes
-    const int h = __ffs(fm) - 1;
-    // binding counters: still <= 1024 before the halving element's update
-    uint32_t bm = 0;
-#pragma unroll
-    for (int k = 0; k < NK; k++) {
-        uint32_t d = (e >> k) + 1u + (uint32_t)k;
-        if ((int32_t)(v[k] - d) <= (int32_t)HALVE_AT) bm |= 1u << k;
-    }
-    bmask = __shfl_sync(0xffffffffu, bm, h);
-#pragma unroll
-    for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, nb[k], h);
-    return commit_epoch(s, w, c, B, h) ? 2 : 4;
-}
 
 __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
-    __shared__ __align__(128) uint4 sfine[2][GROUP];
-    __shared__ __align__(128) uint4 sblk[2][32 * 4];
-    __shared__ __align__(8) uint64_t bars[2];
+    extern __shared__ __align__(128) unsigned char walk_smem[];
+    WalkSmem &WS = *reinterpret_cast<WalkSmem *>(walk_smem);
+    auto &sfine = WS.fine;
+    auto &sblk = WS.blk;
+    uint64_t *bars = WS.bars;
     const uint32_t lane = threadIdx.x;
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    if (lane == 0)
+        for (int b = 0; b < WALK_BUF; b++) mbar_init(&bars[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    uint32_t phase0 = 0, phase1 = 0;   // parity of the next completion of each buffer's barrier
+    uint32_t phases = 0;   // bit b = parity of the next completion of buffer b's barrier
 
     for (;;) {
         uint32_t qi = 0;
@@ -590,94 +461,103 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
         const size_t gbase = (size_t)p * a.cap + cbase;      // global element index of the chain start
         const size_t blk0 = gbase >> 5;                      // global 32-block index
         const uint32_t ep0 = p * a.epcap + cbase / 8 + 16 * cx;
-        WalkChain c;
-        c.rec = a.ep_rec + (size_t)ep0 * 2;
-        c.ep_room = nblk * 4 + 16;                           // records available to this chain
-        c.gbase32 = (uint32_t)gbase;
-        c.count = count;
-        c.lane = lane;
+        uint4 *rec = a.ep_rec + (size_t)ep0 * 2;
+        const uint32_t ep_room = nblk * 4 + 16;              // records available to this chain
+        const uint32_t nwin = (nblk + 31u) >> 5;
 
-        auto prefetch = [&](uint32_t wb, uint32_t buf) {
-            if (lane == 0) {
-                const uint32_t nb = min(nblk - wb, 32u);
-                mbar_expect_tx(&bars[buf], nb * (32u * 16u + 64u));
-                bulk_g2s(&sfine[buf][0], a.fine + gbase + (size_t)wb * 32, nb * 32u * 16u, &bars[buf]);
-                bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + wb) * 4, nb * 64u, &bars[buf]);
-            }
-        };
-        prefetch(0, 0);
-
-        WalkSt s;
+        uint32_t base[NK];
+        uint32_t mintot;
         {
-            uint4 r0 = a.blk_rec4[blk0 * 4], r1 = a.blk_rec4[blk0 * 4 + 1];
-            s.base[0] = 0u - r0.x; s.base[1] = 0u - r0.y; s.base[2] = 0u - r0.z; s.base[3] = 0u - r0.w;
-            s.base[4] = 0u - r1.x; s.base[5] = 0u - r1.y;
+            const uint4 r0 = a.blk_rec4[blk0 * 4], r1 = a.blk_rec4[blk0 * 4 + 1];
+            const uint4 z0 = a.blk_rec4[(blk0 + nblk - 1) * 4 + 2], z1 = a.blk_rec4[(blk0 + nblk - 1) * 4 + 3];
+            base[0] = 0u - r0.x; base[1] = 0u - r0.y; base[2] = 0u - r0.z; base[3] = 0u - r0.w; base[4] = 0u - r1.x; base[5] = 0u - r1.y;
+            mintot = min(min(min(z0.x - r0.x, z0.y - r0.y), min(z0.z - r0.z, z0.w - r0.w)), min(z1.x - r1.x, z1.y - r1.y));
         }
         if (lane == 0) {
-            c.rec[0] = make_uint4(s.base[0], s.base[1], s.base[2], s.base[3]);
-            c.rec[1] = make_uint4(s.base[4], s.base[5], c.gbase32, 0u);
+            rec[0] = make_uint4(base[0], base[1], base[2], base[3]);
+            rec[1] = make_uint4(base[4], base[5], (uint32_t)gbase, 0u);
         }
-        s.nep = 1;
-        s.cur = 0;
-        s.overflow = false;
-        // Candidate binding counters (the ones that pass 1024 last): the two most recently seen.
-        uint32_t c1 = 5, c2 = 5;   // c1 = most recent; set from the first generic epoch
-        bool fast = false;
-        bool finished = false;
+        if (mintot <= HALVE_AT) {
+            // the slowest counter never passes 1024: a single epoch, nothing to walk
+            for (uint32_t b = lane; b < nblk; b += 32) a.blk_epoch[blk0 + b] = ep0;
+            if (lane == 0) rec[3] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+            continue;
+        }
 
-        uint32_t wi = 0;
-        for (uint32_t wb = 0; wb < nblk && !finished; wb += 32, wi++) {
-            const uint32_t buf = wi & 1;
-            if (wb + 32 < nblk) prefetch(wb + 32, buf ^ 1);
-            if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
-            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
-            WalkWin w;
-            w.sfine = &sfine[buf][0];
-            w.sblk = &sblk[buf][0];
-            w.wb = wb;
-            w.valid = wb + lane < nblk;
+        auto prefetch = [&](uint32_t w) {
+            if (lane == 0) {
+                const uint32_t buf = w % WALK_BUF;
+                const uint32_t nb = min(nblk - w * 32u, 32u);
+                mbar_expect_tx(&bars[buf], nb * (32u * 16u + 64u));
+                bulk_g2s(&sfine[buf][0], a.fine + gbase + (size_t)w * GROUP, nb * 32u * 16u, &bars[buf]);
+                bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + w * 32u) * 4, nb * 64u, &bars[buf]);
+            }
+        };
+        for (uint32_t w = 0; w < min(nwin, (uint32_t)WALK_BUF - 1u); w++) prefetch(w);
+
+        uint32_t nep = 1;       // epochs recorded so far
+        uint32_t cur = 0;       // chain-relative first element of the current epoch
+        bool overflow = false;
+        for (uint32_t w = 0; w < nwin; w++) {
+            const uint32_t buf = w % WALK_BUF;
+            if (w + WALK_BUF - 1 < nwin) prefetch(w + WALK_BUF - 1);   // its buffer was consumed in the previous iteration
+            mbar_wait(&bars[buf], (phases >> buf) & 1u);
+            phases ^= 1u << buf;
+            const uint4 *wf = &sfine[buf][0];
+            const uint4 *wb = &sblk[buf][0];
+            const uint32_t wblk0 = w * 32u;
+            const bool valid = wblk0 + lane < nblk;
+            uint32_t incl[NK];
             {
-                uint4 r2 = sblk[buf][lane * 4 + 2], r3 = sblk[buf][lane * 4 + 3];
-                w.incl[0] = r2.x; w.incl[1] = r2.y; w.incl[2] = r2.z; w.incl[3] = r2.w; w.incl[4] = r3.x; w.incl[5] = r3.y;
+                const uint4 r2 = wb[lane * 4 + 2], r3 = wb[lane * 4 + 3];
+                incl[0] = r2.x; incl[1] = r2.y; incl[2] = r2.z; incl[3] = r2.w; incl[4] = r3.x; incl[5] = r3.y;
             }
-            s.my_epoch = s.nep - 1;
-            s.curblk = (int)(s.cur >> 5) - (int)wb;
-            s.blkmask = s.curblk <= 0 ? 0xffffffffu : (s.curblk >= 32 ? 0u : (0xffffffffu << s.curblk));
-            s.lanemask = 0xffffffffu << (s.cur & 31u);
+            uint32_t my_epoch = nep - 1;                              // epoch in effect at the start of my block
+            int curblk = (int)(cur >> 5) - (int)wblk0;                // block (window-relative) holding `cur`
+            uint32_t blkmask = curblk <= 0 ? 0xffffffffu : (curblk >= 32 ? 0u : (0xffffffffu << curblk));
+            uint32_t lanemask = 0xffffffffu << (cur & 31u);
             for (;;) {
-                int r = 1;
-                if (fast) {
-                    // adjacent candidates are searched as a pair, otherwise only the most recent one
-                    const bool pair = (c1 > c2 ? c1 - c2 : c2 - c1) <= 1;
-                    const uint32_t ka = pair ? min(c1, c2) : c1, kb = pair ? max(c1, c2) : c1;
-                    FastSt f;
-                    f.mybase = sel6(s.base, lane & 7u);
-                    f.ba = sel6(s.base, ka); f.bb = sel6(s.base, kb);
-                    f.ia = sel6(w.incl, ka); f.ib = sel6(w.incl, kb);
-                    r = fast_epochs(s, f, w, c, ka, kb);
+                // block level
+                const int32_t bm = min(min(min((int32_t)(base[0] + incl[0]), (int32_t)(base[1] + incl[1])), min((int32_t)(base[2] + incl[2]), (int32_t)(base[3] + incl[3]))),
+                                       min((int32_t)(base[4] + incl[4]), (int32_t)(base[5] + incl[5])));
+                const uint32_t m = __ballot_sync(0xffffffffu, valid && bm > (int32_t)HALVE_AT) & blkmask;
+                if (!m) break;
+                const int B = __ffs(m) - 1;
+                // element level
+                const uint4 f = wf[B * 32 + lane];
+                const uint4 e0 = wb[B * 4], e1 = wb[B * 4 + 1];
+                uint32_t T[NK], v[NK];
+                T[0] = e0.x + (f.x & 0xffffu); T[1] = e0.y + (f.x >> 16); T[2] = e0.z + (f.y & 0xffffu);
+                T[3] = e0.w + (f.y >> 16); T[4] = e1.x + (f.z & 0xffffu); T[5] = e1.y + (f.z >> 16);
 #pragma unroll
-                    for (int k = 0; k < NK; k++) s.base[k] = __shfl_sync(0xffffffffu, f.mybase, k);
-                    if (r == 0) break;
-                    if (r == 2) { finished = true; break; }
+                for (int k = 0; k < NK; k++) v[k] = base[k] + T[k];                  // counters after my element's update
+                const int32_t em = min(min(min((int32_t)v[0], (int32_t)v[1]), min((int32_t)v[2], (int32_t)v[3])), min((int32_t)v[4], (int32_t)v[5]));
+                uint32_t fm = __ballot_sync(0xffffffffu, em > (int32_t)HALVE_AT);
+                if (B == curblk) fm &= lanemask;
+                const int h = __ffs(fm) - 1;                                          // fm != 0: the block's last element passes
+#pragma unroll
+                for (int k = 0; k < NK; k++) base[k] = __shfl_sync(0xffffffffu, (v[k] >> 1) - T[k], h);   // parameter_selection.rs:58-63, re-based
+                cur = (wblk0 + (uint32_t)B) * 32u + (uint32_t)h + 1u;
+                curblk = B + (h == 31 ? 1 : 0);
+                blkmask = curblk >= 32 ? 0u : (0xffffffffu << curblk);
+                lanemask = 0xffffffffu << ((uint32_t)(h + 1) & 31u);
+                if (nep + 1 < ep_room) {
+                    if (lane == 0) {
+                        rec[2 * nep] = make_uint4(base[0], base[1], base[2], base[3]);
+                        rec[2 * nep + 1] = make_uint4(base[4], base[5], (uint32_t)gbase + cur, 0u);
+                    }
+                } else {
+                    overflow = true;
                 }
-                // one epoch on all six counters, then refresh the candidates
-                uint32_t bmask = 0;
-                r = generic_epoch(s, w, c, bmask);
-                if (r == 0) break;
-                if (r == 3) { s.overflow = true; atomicOr(&a.counters[2], 2u); finished = true; break; }
-                const uint32_t hi = 31 - __clz(bmask), lo = __ffs(bmask) - 1;
-                if (hi != lo) { c1 = hi; c2 = lo; }
-                else if (!fast) { c1 = hi; c2 = hi; }          // first epoch of the chain
-                else if (hi != c1) { c2 = c1; c1 = hi; }
-                fast = true;
-                if (r == 2) { finished = true; break; }
+                nep++;
+                if ((int)lane > B) my_epoch++;
             }
-            if (w.valid) a.blk_epoch[blk0 + wb + lane] = ep0 + s.my_epoch;
+            if (valid) a.blk_epoch[blk0 + wblk0 + lane] = ep0 + my_epoch;
             __syncwarp();
         }
         if (lane == 0) {
-            if (s.overflow) atomicOr(&a.counters[2], 1u);
-            else c.rec[2 * s.nep + 1] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // sentinel
+            if (overflow) atomicOr(&a.counters[2], 1u);
+            else rec[2 * nep + 1] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // sentinel
         }
     }
 }
@@ -1065,8 +945,8 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
         L.sp_chain_fail = c.take<uint32_t>(z.max_desc);
         L.sp_sblk = c.take<uint32_t>((size_t)z.max_eb * 8);
         L.sp_ablk = c.take<unsigned long long>((size_t)z.max_eb * 8);
-        L.sp_resolved = c.take<uint8_t>(np * NBIN);
     }
+    L.sp_resolved = c.take<uint8_t>(np * NBIN);
     L.bytes = align_up(c.off, 256);
     return L;
 }
@@ -1172,7 +1052,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_blkfinal<<<(unsigned)((nquarters + 255) / 256), 256, 0, st>>>((uint4 *)L.blk_rec, L.grp_tot, L.super_tot, L.plane_used, g.gpp, nquarters);
                 s.launched(3);
             }
-            const uint8_t *resolved = nullptr;
+            FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_resolved, 0, np * NBIN, st));
             if (L.sp && !ctx->no_spec) {
                 StageScope s(ctx, ST_SPEC);
                 SpArgs sa;
@@ -1188,7 +1068,6 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
                     attr_done = true;
                 }
-                FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_resolved, 0, np * NBIN, st));
                 const SpSizes &z = L.spsz;
                 k_sp_plan<<<1, NBIN, 0, st>>>(sa);
                 k_sp_maps<<<z.max_seg, 1024, sizeof(SpSegSmem), st>>>(sa);
@@ -1200,18 +1079,22 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_finish<<<z.max_eb, 32, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
                 s.launched(9);
-                resolved = L.sp_resolved;
             }
             {
                 StageScope s(ctx, ST_WALK);
                 WalkArgs wa;
-                wa.resolved = resolved;
+                wa.resolved = L.sp_resolved;
                 wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
                 wa.cap = g.cap; wa.epcap = g.epcap;
-                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 6);
-                k_walk<<<blocks, 32, 0, st>>>(wa);
+                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 3);
+                static bool walk_attr_done = false;
+                if (!walk_attr_done) {
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
+                    walk_attr_done = true;
+                }
+                k_walk<<<blocks, 32, sizeof(WalkSmem), st>>>(wa);
                 s.launched();
             }
             {
