@@ -891,7 +891,8 @@ struct Layout {
     bool sp;
     SpSizes spsz;
     SpDesc *sp_desc;
-    uint32_t *sp_seg_desc, *sp_grp_desc, *sp_eb_desc, *sp_counts, *sp_map, *sp_pre, *sp_gmap, *sp_grp_xin, *sp_grp_nbefore, *sp_chain_n, *sp_chain_fail, *sp_sblk;
+    uint32_t *sp_seg_desc, *sp_grp_desc, *sp_eb_desc, *sp_counts, *sp_map, *sp_pre, *sp_gmap, *sp_grp_xin, *sp_grp_nbefore, *sp_chain_n, *sp_chain_fail;
+    uint4 *sp_trow;
     unsigned long long *sp_ablk;
     uint8_t *sp_resolved;
     size_t bytes;
@@ -943,7 +944,7 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
         L.sp_grp_nbefore = c.take<uint32_t>(z.max_grp);
         L.sp_chain_n = c.take<uint32_t>(z.max_desc);
         L.sp_chain_fail = c.take<uint32_t>(z.max_desc);
-        L.sp_sblk = c.take<uint32_t>((size_t)z.max_eb * 8);
+        L.sp_trow = c.take<uint4>(((size_t)np * g.epcap + 8) * 2);
         L.sp_ablk = c.take<unsigned long long>((size_t)z.max_eb * 8);
     }
     L.sp_resolved = c.take<uint8_t>(np * NBIN);
@@ -1059,13 +1060,12 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 sa.chain_count = L.chain_count; sa.chain_base = L.chain_base; sa.fine = L.fine; sa.blk_rec4 = (const uint4 *)L.blk_rec;
                 sa.desc = L.sp_desc; sa.seg_desc = L.sp_seg_desc; sa.grp_desc = L.sp_grp_desc; sa.eb_desc = L.sp_eb_desc; sa.counts = L.sp_counts;
                 sa.map = L.sp_map; sa.pre = L.sp_pre; sa.gmap = L.sp_gmap; sa.grp_xin = L.sp_grp_xin; sa.grp_nbefore = L.sp_grp_nbefore;
-                sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.sblk = L.sp_sblk;
+                sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.trow = L.sp_trow;
                 sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch; sa.resolved = L.sp_resolved; sa.dbg = L.counters;
                 sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz;
                 static bool attr_done = false;
                 if (!attr_done) {
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
-                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
                     attr_done = true;
                 }
                 const SpSizes &z = L.spsz;
@@ -1073,12 +1073,11 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_maps<<<z.max_seg, 1024, sizeof(SpSegSmem), st>>>(sa);
                 k_sp_compose<<<z.max_grp, 1024, 0, st>>>(sa);
                 k_sp_scan<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
-                k_sp_emit<<<z.max_seg, 256, sizeof(SpSegSmem), st>>>(sa);
-                k_sp_blocksum<<<z.max_eb, 32, 0, st>>>(sa);
-                k_sp_blockscan<<<z.max_desc, 32, 0, st>>>(sa);
-                k_sp_finish<<<z.max_eb, 32, 0, st>>>(sa);
+                k_sp_emit<<<(z.max_seg + 3) / 4, 128, 0, st>>>(sa);
+                k_sp_blocksum<<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
+                k_sp_finish<<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
-                s.launched(9);
+                s.launched(8);
             }
             {
                 StageScope s(ctx, ST_WALK);

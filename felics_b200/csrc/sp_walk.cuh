@@ -60,8 +60,8 @@ struct SpArgs {
     uint32_t *grp_nbefore;      // [group slot]: halvings before the group
     uint32_t *chain_n;          // [desc]: halvings in the whole chain
     uint32_t *chain_fail;       // [desc]: SP_OK or a rejection marker
-    unsigned long long *ablk;   // [epoch block][8]
-    uint32_t *sblk;             // [epoch block][8]: counters at the start of the block's first epoch
+    unsigned long long *ablk;   // [epoch block][8]: sum_j D(epoch 32b + j) << j
+    uint4 *trow;                // [epoch record][2]: cost prefixes T0..T5 at the epoch start, start element
     uint4 *ep_rec;
     uint32_t *blk_epoch;
     uint8_t *resolved;          // [plane*512 + context]: 1 when the chain needs no serial walk
@@ -142,23 +142,36 @@ struct SpSegSmem {
     uint16_t inv[SP_INV_CAP];
 };
 
+template <int THREADS>
 __device__ __forceinline__ uint32_t sp_build_segment(SpSegSmem &S, const SpDesc &d, uint32_t seg, const uint4 *__restrict__ fine,
                                                      const uint4 *__restrict__ blk_rec4) {
+    constexpr int PER = SP_SEG / THREADS;
     const uint32_t kb = d.kb;
     const uint32_t e0 = seg * SP_SEG;
     const uint32_t nel = min(d.count - e0, (uint32_t)SP_SEG);
     const uint32_t g0 = d.gbase + e0;   // block aligned
     const uint32_t tstart = reinterpret_cast<const uint32_t *>(blk_rec4 + (size_t)(g0 >> 5) * 4)[kb];
     if (threadIdx.x == 0) S.tk[0] = 0;
-    for (uint32_t j = threadIdx.x; j < nel; j += blockDim.x) {
-        const uint32_t g = g0 + j;
-        const uint32_t excl = reinterpret_cast<const uint32_t *>(blk_rec4 + (size_t)(g >> 5) * 4)[kb];
-        S.tk[j + 1] = excl + reinterpret_cast<const uint16_t *>(fine + g)[kb] - tstart;
+    uint32_t incl[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {      // all loads in flight together
+        const uint32_t j = threadIdx.x + i * THREADS;
+        const uint32_t g = g0 + min(j, nel - 1);
+        incl[i] = reinterpret_cast<const uint32_t *>(blk_rec4 + (size_t)(g >> 5) * 4)[kb] + reinterpret_cast<const uint16_t *>(fine + g)[kb] - tstart;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const uint32_t j = threadIdx.x + i * THREADS;
+        if (j < nel) S.tk[j + 1] = incl[i];
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < nel; j += blockDim.x) {
-        const uint32_t lo = S.tk[j], hi = min(S.tk[j + 1], (uint32_t)SP_INV_CAP);
-        for (uint32_t q = lo; q < hi; q++) S.inv[q] = (uint16_t)j;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const uint32_t j = threadIdx.x + i * THREADS;
+        if (j < nel) {
+            const uint32_t lo = S.tk[j], hi = min(incl[i], (uint32_t)SP_INV_CAP);
+            for (uint32_t q = lo; q < hi; q++) S.inv[q] = (uint16_t)j;
+        }
     }
     __syncthreads();
     return nel;
@@ -182,18 +195,32 @@ __global__ void __launch_bounds__(1024) k_sp_maps(SpArgs a) {
     if (slot >= a.counts[1]) return;
     const SpDesc d = a.desc[a.seg_desc[slot]];
     const uint32_t seg = slot - d.seg0;
-    const uint32_t nel = sp_build_segment(S, d, seg, a.fine, a.blk_rec4);
-    for (uint32_t x0 = threadIdx.x; x0 < SP_DOM; x0 += blockDim.x) {
-        uint32_t x = x0, p = 0, n = 0;
+    const uint32_t nel = sp_build_segment<1024>(S, d, seg, a.fine, a.blk_rec4);
+    const uint32_t tend = S.tk[nel];
+    auto run = [&](uint32_t x0) {
+        uint32_t x = x0, p = 0, tp = 0, n = 0;   // tp = tk[p]
         for (;;) {
-            const uint32_t j = sp_next_halving(S, nel, p, x);
-            if (j >= nel) { x += S.tk[nel] - S.tk[p]; break; }
-            x = (x + S.tk[j + 1] - S.tk[p]) >> 1;
+            const uint32_t q = tp + (HALVE_AT - x);          // next halving: first j with tk[j + 1] > q
+            if (q >= tend) { x += tend - tp; break; }
+            uint32_t j;
+            if (q < (uint32_t)SP_INV_CAP) {
+                j = S.inv[q];
+            } else {                                          // beyond the table: bisection
+                uint32_t lo = p, hi = nel - 1;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (S.tk[mid + 1] > q) hi = mid; else lo = mid + 1; }
+                j = lo;
+            }
+            const uint32_t t1 = S.tk[j + 1];
+            x = (x + t1 - tp) >> 1;
+            tp = t1;
             p = j + 1;
             n++;
         }
         a.map[(size_t)slot * SP_DOM + x0] = x | (n << 16);
-    }
+    };
+    // a counter is at least 1 at every segment boundary but the chain start, so x = 0 only matters for segment 0
+    run(threadIdx.x + 1);
+    if (seg == 0 && threadIdx.x == 0) run(0);
 }
 
 // 2. compose the maps of 32 consecutive segments; pre[] keeps the state at every segment start
@@ -204,6 +231,7 @@ __global__ void __launch_bounds__(1024) k_sp_compose(SpArgs a) {
     const uint32_t g = gslot - d.grp0;
     const uint32_t s0 = g * SP_GRP, s1 = min(s0 + SP_GRP, d.nseg);
     for (uint32_t x0 = threadIdx.x; x0 < SP_DOM; x0 += blockDim.x) {
+        if (x0 == 0 && g != 0) continue;   // x = 0 exists only at the chain start
         uint32_t x = x0, n = 0;
         for (uint32_t s = s0; s < s1; s++) {
             a.pre[(size_t)(d.seg0 + s) * SP_DOM + x0] = x | (n << 16);   // n <= 32 * 4096 / 2 fits 16 bits only if epochs >= 2 elements: checked in k_sp_scan
@@ -235,45 +263,70 @@ __global__ void k_sp_scan(SpArgs a) {
     a.chain_fail[di] = (!sat && n + 2 < d.ep_room) ? SP_OK : 0u;
 }
 
-// 4. re-walk every segment from its true x_in and write the epoch starts
-__global__ void __launch_bounds__(256) k_sp_emit(SpArgs a) {
-    extern __shared__ __align__(16) unsigned char sp_smem[];
-    SpSegSmem &S = *reinterpret_cast<SpSegSmem *>(sp_smem);
-    const uint32_t slot = blockIdx.x;
+// 4. re-walk every segment from its true x_in (one warp per segment, two-level search straight from global
+//    memory: block-end prefixes, then the 32 elements of the block found); for every epoch that starts inside
+//    the segment write the start element and the six cost prefixes at the start (trow)
+__global__ void __launch_bounds__(128) k_sp_emit(SpArgs a) {
+    const uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (slot >= a.counts[1]) return;
     const uint32_t di = a.seg_desc[slot];
     if (a.chain_fail[di] != SP_OK) return;
     const SpDesc d = a.desc[di];
-    const uint32_t seg = slot - d.seg0;
-    const uint32_t nel = sp_build_segment(S, d, seg, a.fine, a.blk_rec4);
-    if (threadIdx.x == 0) {
-        const uint32_t g = seg / SP_GRP;
-        const uint32_t pr = a.pre[(size_t)slot * SP_DOM + a.grp_xin[d.grp0 + g]];
-        uint32_t x = pr & 0xffffu, n = a.grp_nbefore[d.grp0 + g] + (pr >> 16), p = 0;
-        uint32_t *rec32 = reinterpret_cast<uint32_t *>(a.ep_rec + (size_t)d.ep0 * 2);
-        for (;;) {
-            const uint32_t j = sp_next_halving(S, nel, p, x);
-            if (j >= nel) break;
-            x = (x + S.tk[j + 1] - S.tk[p]) >> 1;
-            p = j + 1;
-            n++;
-            rec32[(size_t)n * 8 + 6] = d.gbase + seg * SP_SEG + p;   // first element of epoch n
+    const uint32_t seg = slot - d.seg0, kb = d.kb;
+    const uint32_t e0 = seg * SP_SEG;
+    const uint32_t nel = min(d.count - e0, (uint32_t)SP_SEG);
+    const uint32_t g0 = d.gbase + e0, b0 = g0 >> 5, nblk = (nel + 31u) >> 5;
+    const uint32_t tstart = reinterpret_cast<const uint32_t *>(a.blk_rec4 + (size_t)b0 * 4)[kb];
+    uint32_t tend[SP_SEG / 1024];          // relative prefix at the end of blocks lane, lane + 32, ...
+#pragma unroll
+    for (int i = 0; i < SP_SEG / 1024; i++) {
+        const uint32_t b = lane + 32u * i;
+        tend[i] = b < nblk ? reinterpret_cast<const uint32_t *>(a.blk_rec4 + (size_t)(b0 + b) * 4)[8 + kb] - tstart : 0u;
+    }
+    uint4 *rows = a.trow + (size_t)d.ep0 * 2;
+    if (seg == 0 && lane == 0) {
+        const uint4 r0 = a.blk_rec4[(size_t)b0 * 4], r1 = a.blk_rec4[(size_t)b0 * 4 + 1];
+        rows[0] = r0;
+        rows[1] = make_uint4(r1.x, r1.y, d.gbase, 0u);
+    }
+    const uint32_t grp = seg / SP_GRP;
+    const uint32_t pr = a.pre[(size_t)slot * SP_DOM + a.grp_xin[d.grp0 + grp]];
+    uint32_t x = pr & 0xffffu, n = a.grp_nbefore[d.grp0 + grp] + (pr >> 16), tp = 0;
+    for (;;) {
+        const uint32_t q = tp + (HALVE_AT - x);              // next halving: first element whose inclusive prefix passes q
+        int B = -1;
+#pragma unroll
+        for (int i = 0; i < SP_SEG / 1024; i++) {
+            if (B < 0) {
+                const uint32_t m = __ballot_sync(0xffffffffu, lane + 32u * i < nblk && tend[i] > q);
+                if (m) B = 32 * i + __ffs(m) - 1;
+            }
+        }
+        if (B < 0) break;
+        const uint32_t g = g0 + (uint32_t)B * 32u + lane;
+        const uint4 f = a.fine[g];
+        const uint4 x0 = a.blk_rec4[(size_t)(b0 + B) * 4], x1 = a.blk_rec4[(size_t)(b0 + B) * 4 + 1];
+        const uint32_t T[NK] = {x0.x + (f.x & 0xffffu), x0.y + (f.x >> 16), x0.z + (f.y & 0xffffu), x0.w + (f.y >> 16), x1.x + (f.z & 0xffffu), x1.y + (f.z >> 16)};
+        uint32_t tkb = T[0];
+        tkb = kb == 1 ? T[1] : tkb; tkb = kb == 2 ? T[2] : tkb; tkb = kb == 3 ? T[3] : tkb; tkb = kb == 4 ? T[4] : tkb; tkb = kb == 5 ? T[5] : tkb;
+        tkb -= tstart;
+        const uint32_t m = __ballot_sync(0xffffffffu, (uint32_t)B * 32u + lane < nel && tkb > q);
+        if (!m) { atomicMin(&a.chain_fail[di], 0u); break; }   // cannot happen: the block's last element passes
+        const int h = __ffs(m) - 1;
+        const uint32_t t1 = __shfl_sync(0xffffffffu, tkb, h);
+        x = (x + t1 - tp) >> 1;
+        tp = t1;
+        n++;
+        if ((int)lane == h) {                                   // epoch n starts right after my element
+            rows[(size_t)n * 2] = make_uint4(T[0], T[1], T[2], T[3]);
+            rows[(size_t)n * 2 + 1] = make_uint4(T[4], T[5], g + 1u, 0u);
         }
     }
 }
 
-// start (global element index) of epoch e of a chain; epoch 0 starts at the chain start
-__device__ __forceinline__ uint32_t sp_epoch_start(const SpArgs &a, const SpDesc &d, uint32_t e) {
-    if (e == 0) return d.gbase;
-    return reinterpret_cast<const uint32_t *>(a.ep_rec + (size_t)d.ep0 * 2)[(size_t)e * 8 + 6];
-}
-__device__ __forceinline__ uint32_t sp_prefix_at(const SpArgs &a, const SpDesc &d, uint32_t g, uint32_t k) {
-    return g == d.gbase ? sp_prefix_chain_start(a.blk_rec4, g, k) : sp_prefix_end(a.fine, a.blk_rec4, g, k);
-}
-
 // 5. per block of 32 epochs: A[k] = sum_j D_k(epoch 32b + j) << j   (D = cost of the whole epoch)
-__global__ void __launch_bounds__(32) k_sp_blocksum(SpArgs a) {
-    const uint32_t slot = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(128) k_sp_blocksum(SpArgs a) {
+    const uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (slot >= a.counts[3]) return;
     const uint32_t di = a.eb_desc[slot];
     if (a.chain_fail[di] != SP_OK) return;
@@ -286,12 +339,11 @@ __global__ void __launch_bounds__(32) k_sp_blocksum(SpArgs a) {
 #pragma unroll
     for (int k = 0; k < NK; k++) acc[k] = 0;
     if (e < n) {
-        const uint32_t s0 = sp_epoch_start(a, d, e), s1 = sp_epoch_start(a, d, e + 1);
+        const uint4 *r = a.trow + (size_t)(d.ep0 + e) * 2;
+        const uint4 a0 = r[0], a1 = r[1], b0 = r[2], b1 = r[3];
+        const uint32_t D[NK] = {b0.x - a0.x, b0.y - a0.y, b0.z - a0.z, b0.w - a0.w, b1.x - a1.x, b1.y - a1.y};
 #pragma unroll
-        for (int k = 0; k < NK; k++) {
-            const uint32_t D = sp_prefix_end(a.fine, a.blk_rec4, s1, k) - sp_prefix_at(a, d, s0, k);
-            acc[k] = (unsigned long long)D << lane;
-        }
+        for (int k = 0; k < NK; k++) acc[k] = (unsigned long long)D[k] << lane;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -305,33 +357,28 @@ __global__ void __launch_bounds__(32) k_sp_blocksum(SpArgs a) {
     }
 }
 
-// 6. serial over the 32-epoch blocks of one chain: S <- (S + A) >> 32, exactly the 32 halvings
-__global__ void __launch_bounds__(32) k_sp_blockscan(SpArgs a) {
-    const uint32_t di = blockIdx.x, lane = threadIdx.x;
-    if (di >= a.counts[0]) return;
-    if (a.chain_fail[di] != SP_OK) return;
-    const SpDesc d = a.desc[di];
-    const uint32_t n = a.chain_n[di];
-    const uint32_t nfull = n / 32;               // blocks whose 32 epochs all end with a halving
-    if (lane >= 8) return;
-    const unsigned long long *__restrict__ A = a.ablk + (size_t)d.eb0 * 8 + lane;
-    uint32_t *__restrict__ out = a.sblk + (size_t)d.eb0 * 8 + lane;
-    unsigned long long S = 0;
-    uint32_t b = 0;
-    out[0] = 0;
-    for (; b + 8 <= nfull; b += 8) {             // loads do not depend on S: batch them
-        unsigned long long v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = A[(size_t)(b + i) * 8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) { S = (S + v[i]) >> 32; out[(size_t)(b + i + 1) * 8] = (uint32_t)S; }
+// Counter k at the start of epoch 32b of a chain: S_{b} = (S_{b-1} + A_{b-1}) >> 32 = hi(A_{b-1}) + carry, where the
+// carry out of the low word depends on S_{b-1} only when lo(A_{b-1}) + hi(A_{b-2}) is exactly 2^32 - 1; the look-back
+// stops as soon as the carry is certain (block 0 starts from zero).  Exact, and parallel over the blocks.
+__device__ __forceinline__ uint32_t sp_block_start(const unsigned long long *__restrict__ A /* ablk of the chain, slot k */, uint32_t b) {
+    if (b == 0) return 0;
+    // find the newest block c <= b - 1 whose incoming state does not matter, then run forward
+    uint32_t c = b - 1;
+    for (;;) {
+        if (c == 0) break;                                   // S_0 = 0 is known
+        const unsigned long long lo = A[(size_t)c * 8] & 0xffffffffull, hi_prev = A[(size_t)(c - 1) * 8] >> 32;
+        // S_c is hi_prev or hi_prev + 1: the carry of block c is certain unless lo + hi_prev == 2^32 - 1
+        if (lo + hi_prev != 0xffffffffull) break;
+        c--;
     }
-    for (; b < nfull; b++) { S = (S + A[(size_t)b * 8]) >> 32; out[(size_t)(b + 1) * 8] = (uint32_t)S; }
+    unsigned long long S = c == 0 ? 0ull : (A[(size_t)(c - 1) * 8] >> 32);   // exact when c == 0, else a value whose carry effect on block c is the same as the true one
+    for (uint32_t i = c; i < b; i++) S = (S + A[(size_t)i * 8]) >> 32;
+    return (uint32_t)S;
 }
 
-// 7. per block of 32 epochs: exact counters at every epoch start, verification, epoch records, block epochs
-__global__ void __launch_bounds__(32) k_sp_finish(SpArgs a) {
-    const uint32_t slot = blockIdx.x, lane = threadIdx.x;
+// 6. per block of 32 epochs: exact counters at every epoch start, verification, epoch records, block epochs
+__global__ void __launch_bounds__(128) k_sp_finish(SpArgs a) {
+    const uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (slot >= a.counts[3]) return;
     const uint32_t di = a.eb_desc[slot];
     const uint32_t fail = a.chain_fail[di];
@@ -348,14 +395,24 @@ __global__ void __launch_bounds__(32) k_sp_finish(SpArgs a) {
 #pragma unroll
     for (int k = 0; k < NK; k++) { T0[k] = 0; D[k] = 0; pre[k] = 0; }
     if (has_epoch) {
-        s0 = sp_epoch_start(a, d, e);
-        s1 = has_halving ? sp_epoch_start(a, d, e + 1) : d.gbase + d.count;
+        const uint4 *r = a.trow + (size_t)(d.ep0 + e) * 2;
+        const uint4 a0 = r[0], a1 = r[1];
+        T0[0] = a0.x; T0[1] = a0.y; T0[2] = a0.z; T0[3] = a0.w; T0[4] = a1.x; T0[5] = a1.y;
+        s0 = a1.z;
+        if (has_halving) {
+            const uint4 b0 = r[2], b1 = r[3];
+            D[0] = b0.x - a0.x; D[1] = b0.y - a0.y; D[2] = b0.z - a0.z; D[3] = b0.w - a0.w; D[4] = b1.x - a1.x; D[5] = b1.y - a1.y;
+            s1 = b1.z;
+        } else {
+            s1 = d.gbase + d.count;
+            if (s1 > s0) {
 #pragma unroll
-        for (int k = 0; k < NK; k++) {
-            T0[k] = sp_prefix_at(a, d, s0, k);
-            if (s1 > s0) D[k] = sp_prefix_end(a.fine, a.blk_rec4, s1, k) - T0[k];
-            if (has_halving) pre[k] = (unsigned long long)D[k] << lane;
+                for (int k = 0; k < NK; k++) D[k] = sp_prefix_end(a.fine, a.blk_rec4, s1, k) - T0[k];
+            }
         }
+#pragma unroll
+        for (int k = 0; k < NK; k++)
+            if (has_halving) pre[k] = (unsigned long long)D[k] << lane;
     }
     // inclusive prefix over the lanes: sum_{i <= lane} D_i << i
 #pragma unroll
@@ -366,12 +423,16 @@ __global__ void __launch_bounds__(32) k_sp_finish(SpArgs a) {
             if (lane >= (uint32_t)o) pre[k] += t;
         }
     }
+    // counters at the start of the block's first epoch: lane k computes counter k, then broadcast
+    uint32_t sb = 0;
+    if (lane < NK) sb = sp_block_start(a.ablk + (size_t)d.eb0 * 8 + lane, b);
     bool bad = false;
     uint32_t S[NK];
 #pragma unroll
     for (int k = 0; k < NK; k++) {
+        const unsigned long long sblk = __shfl_sync(0xffffffffu, sb, k);
         const unsigned long long excl = pre[k] - (has_halving ? ((unsigned long long)D[k] << lane) : 0ull);
-        S[k] = (uint32_t)(((unsigned long long)a.sblk[(size_t)slot * 8 + k] + excl) >> lane);   // counters at the start of my epoch
+        S[k] = (uint32_t)((sblk + excl) >> lane);                                                // counters at the start of my epoch
         if (has_halving && !((int32_t)(S[k] + D[k]) > (int32_t)HALVE_AT)) bad = true;           // every counter must be past 1024 after the halving element
     }
     uint32_t vkb = S[0] + D[0];
