@@ -70,7 +70,7 @@ struct BitReader {
     }
 };
 
-__global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
+__global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
     __shared__ uint32_t tab[(NBIN - 1) * NK];
     const uint32_t img = blockIdx.x;
     if (img >= n) return;
@@ -181,6 +181,216 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
     if (lane == 0) a.status[img] = st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path: rows up to DEC_MAX_W samples.  Lane 0 is the decoder; everything it touches per pixel is
+// on chip: the bit stream sits in a 64-bit register window refilled from words that were loaded 4..8
+// words ahead, the previous and the current row live in shared memory (the left neighbour in a
+// register), the estimator table (511 x 6 counters) in shared memory.  The warp writes each finished
+// row to global memory with coalesced stores.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t DEC_MAX_W = 32768;
+
+struct BitWindow {
+    const uint32_t *words;
+    uint64_t nwords;
+    uint64_t wi;          // next word to feed into the window
+    uint64_t win;         // unread bits, MSB first
+    int navail;           // valid bits in win
+    uint64_t used, limit; // bits consumed so far / bits in the file after the header
+    uint32_t c[4], nx[4]; // current group of 4 words and the prefetched next group (already byte-swapped)
+
+    __device__ __forceinline__ uint32_t load(uint64_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
+    __device__ __forceinline__ void load_group(uint32_t g[4], uint64_t first) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = load(first + i);
+    }
+    __device__ __forceinline__ void init(const uint32_t *w, uint64_t nw, uint64_t bitpos, uint64_t bitend) {
+        words = w; nwords = nw; used = 0; limit = bitend - bitpos;
+        wi = bitpos >> 5;
+        const uint32_t sh = (uint32_t)(bitpos & 31);
+        const uint64_t g0 = wi & ~3ull;
+        load_group(c, g0);
+        load_group(nx, g0 + 4);
+        win = 0; navail = 0;
+        const uint32_t first = next_word();
+        win = (uint64_t)(first << sh) << 32;
+        navail = 32 - (int)sh;
+        refill();
+    }
+    __device__ __forceinline__ uint32_t next_word() {
+        const uint32_t idx = (uint32_t)(wi & 3);
+        uint32_t v = c[0];
+        v = idx == 1 ? c[1] : v; v = idx == 2 ? c[2] : v; v = idx == 3 ? c[3] : v;
+        wi++;
+        if ((wi & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) c[i] = nx[i];
+            load_group(nx, wi + 4);
+        }
+        return v;
+    }
+    // keep more than 32 valid bits in the window
+    __device__ __forceinline__ void refill() {
+        if (navail <= 32) {
+            win |= (uint64_t)next_word() << (32 - navail);
+            navail += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(win >> 32); }
+    __device__ __forceinline__ void skip(int n) { win <<= n; navail -= n; used += (uint32_t)n; }   // n <= 32, window refilled before
+    __device__ __forceinline__ uint32_t read(int n) {   // n in 0..32
+        if (n == 0) return 0;
+        const uint32_t v = peek32() >> (32 - n);
+        skip(n);
+        refill();
+        return v;
+    }
+    __device__ __forceinline__ bool eof() const { return used > limit; }
+};
+
+__global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
+    extern __shared__ __align__(16) unsigned char dec_smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(dec_smem);                         // [(NBIN-1) * NK]
+    int16_t *rows = reinterpret_cast<int16_t *>(dec_smem + (NBIN - 1) * NK * 4 + 8);  // [2][w]
+    const uint32_t img = blockIdx.x;
+    if (img >= n) return;
+    const uint32_t lane = threadIdx.x;
+    const uint64_t off0 = a.offsets[img], off1 = a.offsets[img + 1];
+    const uint64_t len = off1 - off0;
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(a.words);
+    int st = FELICS_OK;
+    // read_header order (format.rs:63-84), then decompress_with_header's checks (compression.rs:289-294)
+    if (lane == 0) {
+        const uint8_t *hb = bytes + off0;
+        if (len < 4) st = FELICS_ERR_IO;
+        else if (hb[0] != 'F' || hb[1] != 'L' || hb[2] != 'C' || hb[3] != 'S') st = FELICS_ERR_INVALID_SIGNATURE;
+        else if (len < 5) st = FELICS_ERR_IO;
+        else if (hb[4] > 1) st = FELICS_ERR_INVALID_COLOR_TYPE;
+        else if (len < 6) st = FELICS_ERR_IO;
+        else if (hb[5] > 1) st = FELICS_ERR_INVALID_PIXEL_DEPTH;
+        else if (len < FELICS_HEADER_BYTES) st = FELICS_ERR_IO;
+        else if (hb[4] != a.color) st = FELICS_ERR_INVALID_COLOR_TYPE;
+        else if (hb[5] != a.depth) st = FELICS_ERR_INVALID_PIXEL_DEPTH;
+        else {
+            uint32_t w = ((uint32_t)hb[6] << 24) | ((uint32_t)hb[7] << 16) | ((uint32_t)hb[8] << 8) | hb[9];
+            uint32_t h = ((uint32_t)hb[10] << 24) | ((uint32_t)hb[11] << 16) | ((uint32_t)hb[12] << 8) | hb[13];
+            if (w != a.w || h != a.h) st = FELICS_ERR_INVALID_DIMENSIONS;
+        }
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st != FELICS_OK) { if (lane == 0) a.status[img] = st; return; }
+
+    const uint32_t w = a.w, h = a.h;
+    BitWindow br;
+    if (lane == 0) br.init(a.words, a.arena_words, 8 * (off0 + FELICS_HEADER_BYTES), 8 * off1);
+
+    for (uint32_t ch = 0; ch < a.nch && st == FELICS_OK; ch++) {
+        for (uint32_t j = lane; j < (NBIN - 1) * NK; j += 32) tab[j] = 0;   // fresh estimator per channel (:186-190)
+        __syncwarp();
+        int16_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.npix;
+        int32_t p1 = 0, p2 = 0;
+        if (lane == 0) {
+            p1 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
+            p2 = (int32_t)br.read(32);
+            if (br.eof()) st = FELICS_ERR_IO;
+            else if (a.npix >= 1 && (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767)))) st = FELICS_ERR_INVALID_VALUE;
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        if (st != FELICS_OK || a.npix == 0) continue;
+        int col0_a = 0, col0_b = 0;   // samples at x = 0 of the previous row and of the row before it
+        for (uint32_t y = 0; y < h && st == FELICS_OK; y++) {
+            int16_t *cur = rows + (size_t)(y & 1u) * w;
+            const int16_t *up = rows + (size_t)((y & 1u) ^ 1u) * w;
+            if (lane == 0) {
+                uint32_t x = 0;
+                int left = 0, left2 = 0;
+                if (y == 0) {
+                    cur[0] = (int16_t)p1; left = p1;
+                    x = 1;
+                    if (w >= 2) { cur[1] = (int16_t)p2; left2 = p1; left = p2; x = 2; }
+                } else if (y == 1 && w == 1) {
+                    cur[0] = (int16_t)p2; x = 1;          // 1-wide image: the second raw sample is (0, 1)
+                }
+                for (; x < w; x++) {
+                    int v1, v2;
+                    if (x > 0 && y > 0) { v1 = left; v2 = up[x]; }              // left, up
+                    else if (y == 0) { v1 = left; v2 = left2; }                 // first row: i-1, i-2
+                    else if (y >= 2) { v1 = col0_a; v2 = col0_b; }              // first column: up, up-up
+                    else { v1 = up[0]; v2 = up[1]; }                            // (0,1): up, up-right
+                    const int hi = max(v1, v2), lo = min(v1, v2);
+                    const uint32_t ctx = (uint32_t)(hi - lo);
+                    if (ctx > 510u) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
+                    const uint32_t top = br.peek32();
+                    int value;
+                    if (top >> 31) {                                        // InRange (:208-215)
+                        const uint32_t nn = ctx + 1;
+                        const int m = 31 - __clz(nn);
+                        const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                        // marker + m bits (+ 1): at most 11 bits, all inside the window
+                        uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;
+                        int used = 1 + m;
+                        if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
+                        br.skip(used);
+                        br.refill();
+                        xx += left_p;                                       // rotate_left (:55-57)
+                        if (xx >= nn) xx -= nn;
+                        if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
+                        value = lo + (int)xx;
+                    } else {
+                        const uint32_t above = (top >> 30) & 1u;
+                        uint32_t *row = tab + ctx * NK;
+                        const uint2 r01 = *reinterpret_cast<const uint2 *>(row), r23 = *reinterpret_cast<const uint2 *>(row + 2), r45 = *reinterpret_cast<const uint2 *>(row + 4);
+                        uint32_t rr[NK] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y};
+                        const int k = argmin_last(rr);                      // get_k (:202)
+                        br.skip(2);
+                        br.refill();
+                        uint32_t q = 0;                                     // read_unary0
+                        for (;;) {
+                            const uint32_t ones = __clz(~br.peek32());      // 32 when all ones
+                            if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
+                            q += 32; br.skip(32); br.refill();
+                            if (br.eof()) break;
+                        }
+                        const uint32_t rem = br.read(k);
+                        if (br.eof()) { st = FELICS_ERR_IO; break; }
+                        if (q > 70000u) { st = FELICS_ERR_INVALID_VALUE; break; }
+                        const uint32_t e = (q << k) + rem;
+                        uint32_t mn = 0xffffffffu;
+#pragma unroll
+                        for (int kk = 0; kk < NK; kk++) {                   // update (parameter_selection.rs:49-65)
+                            rr[kk] += (e >> kk) + 1u + (uint32_t)kk;
+                            mn = min(mn, rr[kk]);
+                        }
+                        if (mn > HALVE_AT) {
+#pragma unroll
+                            for (int kk = 0; kk < NK; kk++) rr[kk] >>= 1;
+                        }
+                        *reinterpret_cast<uint2 *>(row) = make_uint2(rr[0], rr[1]);
+                        *reinterpret_cast<uint2 *>(row + 2) = make_uint2(rr[2], rr[3]);
+                        *reinterpret_cast<uint2 *>(row + 4) = make_uint2(rr[4], rr[5]);
+                        value = above ? hi + (int)e + 1 : lo - (int)e - 1;  // (:216-243)
+                    }
+                    if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
+                    cur[x] = (int16_t)value;
+                    left2 = left;
+                    left = value;
+                }
+                if (br.eof()) st = FELICS_ERR_IO;   // the reference fails at the read that runs out of input, before any later check
+                col0_b = col0_a;
+                col0_a = cur[0];
+            }
+            st = __shfl_sync(0xffffffffu, st, 0);
+            __syncwarp();
+            if (st == FELICS_OK) {
+                int16_t *dst = pl + (size_t)y * w;
+                for (uint32_t x = lane; x < w; x += 32) dst[x] = cur[x];
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) a.status[img] = st;
+}
+
 // planes -> pixels with the try_into range checks (compression.rs:305-310, :402-407)
 __global__ void k_unplane_gray8(const int16_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, size_t total,
                                 int *__restrict__ status) {
@@ -251,7 +461,17 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     a.color = hdr.color_type; a.depth = hdr.pixel_depth;
     {
         StageScope s(ctx, ST_DECODE);
-        k_decode<<<(unsigned)n, 32, 0, st>>>(a, (uint32_t)n);
+        const size_t smem = (size_t)(NBIN - 1) * NK * 4 + 8 + 2 * (size_t)hdr.width * sizeof(int16_t);
+        if (hdr.width <= DEC_MAX_W && npix >= 1) {
+            static size_t attr_set = 0;
+            if (smem > 48 * 1024 && smem > attr_set) {
+                FELICS_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_set = smem;
+            }
+            k_decode<<<(unsigned)n, 32, smem, st>>>(a, (uint32_t)n);
+        } else {
+            k_decode_wide<<<(unsigned)n, 32, 0, st>>>(a, (uint32_t)n);   // very wide rows (or empty images): neighbours from global memory
+        }
         s.launched();
     }
     if (npix > 0) {
