@@ -26,9 +26,9 @@ struct PixelClass {
     int lo;
 };
 
-__device__ __forceinline__ PixelClass classify_pixel(const int16_t *__restrict__ pl, uint32_t i, uint32_t w) {
-    uint32_t y = i / w;
-    uint32_t x = i - y * w;
+// T = uint8_t (gray samples straight from the caller's pixels) or int16_t (Y/Co/Cg planes).
+template <typename T>
+__device__ __forceinline__ PixelClass classify_pixel_xy(const T *__restrict__ pl, uint32_t i, uint32_t x, uint32_t y, uint32_t w) {
     uint32_t a, b;
     if (x > 0 && y > 0) { a = i - 1; b = i - w; }            // left, up
     else if (y == 0) { a = i - 1; b = i - 2; }               // first row (x >= 2 because i >= 2)
@@ -43,6 +43,21 @@ __device__ __forceinline__ PixelClass classify_pixel(const int16_t *__restrict__
     else if (p > h) { r.cls = 1; r.val = p - h - 1; }
     else { r.cls = 0; r.val = p - l; }
     return r;
+}
+template <typename T>
+__device__ __forceinline__ PixelClass classify_pixel(const T *__restrict__ pl, uint32_t i, uint32_t w) {
+    uint32_t y = i / w;
+    return classify_pixel_xy(pl, i, i - y * w, y, w);
+}
+// raster position (x, y) of pixel i after moving `step` pixels forward; one division only for narrow images
+__device__ __forceinline__ void advance_xy(uint32_t &x, uint32_t &y, uint32_t i_new, uint32_t step, uint32_t w) {
+    if (w >= step) {
+        x += step;
+        if (x >= w) { x -= w; y++; }
+    } else {
+        y = i_new / w;
+        x = i_new - y * w;
+    }
 }
 
 // Phased-in code of v in [0, n-1] (phase_in_coding.rs:23-84): returns the code value, sets len.

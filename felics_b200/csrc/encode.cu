@@ -29,12 +29,6 @@ namespace felics {
 // ------------------------------------------------------------------------------------
 // planes
 // ------------------------------------------------------------------------------------
-__global__ void k_to_planes_gray8(const uint8_t *__restrict__ px, int16_t *__restrict__ planes, size_t total) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) planes[i] = (int16_t)px[i];
-}
-
 // color_transform.rs:11-17; C++ int division truncates toward zero like Rust's.
 __global__ void k_to_planes_rgb8(const uint8_t *__restrict__ px, int16_t *__restrict__ planes, uint32_t npix, size_t total) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,7 +51,8 @@ __global__ void k_to_planes_rgb8(const uint8_t *__restrict__ px, int16_t *__rest
 // ------------------------------------------------------------------------------------
 // hist: one block per tile
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_THREADS) k_hist(const int16_t *__restrict__ planes, uint32_t w, uint32_t npix,
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS) k_hist(const T *__restrict__ planes, uint32_t w, uint32_t npix,
                                                        uint32_t tpp, uint32_t nchunks, uint32_t *__restrict__ tile_hist,
                                                        uint32_t *__restrict__ chunk_tot) {
     __shared__ uint32_t h[NBIN];
@@ -65,15 +60,18 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist(const int16_t *__restrict
     uint32_t p = bid / tpp, t = bid - p * tpp;
     for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) h[c] = 0;
     __syncthreads();
-    const int16_t *pl = planes + (size_t)p * npix;
+    const T *pl = planes + (size_t)p * npix;
     uint32_t start = t * TILE;
+    uint32_t i = start + threadIdx.x;
+    uint32_t y = i / w, x = i - y * w;
 #pragma unroll 4
     for (int j = 0; j < TILE / TILE_THREADS; j++) {
-        uint32_t i = start + j * TILE_THREADS + threadIdx.x;
         if (i >= 2 && i < npix) {
-            PixelClass pc = classify_pixel(pl, i, w);
+            PixelClass pc = classify_pixel_xy(pl, i, x, y, w);
             if (pc.cls != 0) atomicAdd(&h[pc.delta], 1u);
         }
+        i += TILE_THREADS;
+        advance_xy(x, y, i, TILE_THREADS, w);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) {
@@ -139,10 +137,18 @@ __global__ void __launch_bounds__(NBIN) k_tilebase(uint32_t *__restrict__ tile_h
     uint32_t p = bid / nchunks, ch = bid - p * nchunks, c = threadIdx.x;
     uint32_t run = chunk_tot[(size_t)bid * NBIN + c] + chain_base[(size_t)p * NBIN + c];
     uint32_t t0 = ch * CHUNK_TILES, t1 = min(t0 + CHUNK_TILES, tpp);
-    for (uint32_t t = t0; t < t1; t++) {
-        size_t idx = ((size_t)p * tpp + t) * NBIN + c;
-        uint32_t v = tile_hist[idx];
-        tile_hist[idx] = run;
+    uint32_t *col = tile_hist + ((size_t)p * tpp) * NBIN + c;
+    uint32_t t = t0;
+    for (; t + 8 <= t1; t += 8) {        // eight independent loads in flight
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = col[(size_t)(t + q) * NBIN];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { col[(size_t)(t + q) * NBIN] = run; run += v[q]; }
+    }
+    for (; t < t1; t++) {
+        uint32_t v = col[(size_t)t * NBIN];
+        col[(size_t)t * NBIN] = run;
         run += v;
     }
 }
@@ -151,7 +157,8 @@ __global__ void __launch_bounds__(NBIN) k_tilebase(uint32_t *__restrict__ tile_h
 // scatter: stable grouping by context.  Warp w owns pixels [512w, 512w+512) of the tile
 // and visits them 32 consecutive pixels at a time, so ranks follow raster order.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_THREADS) k_scatter(const int16_t *__restrict__ planes, uint32_t w, uint32_t npix,
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS) k_scatter(const T *__restrict__ planes, uint32_t w, uint32_t npix,
                                                           uint32_t tpp, uint32_t cap, const uint32_t *__restrict__ tile_base,
                                                           uint16_t *__restrict__ e_grp, uint32_t *__restrict__ gidx) {
     __shared__ uint16_t wcnt[TILE_WARPS][NBIN];
@@ -161,18 +168,19 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const int16_t *__restr
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int c = threadIdx.x; c < TILE_WARPS * NBIN; c += TILE_THREADS) (&wcnt[0][0])[c] = 0;
     __syncthreads();
-    const int16_t *pl = planes + (size_t)p * npix;
+    const T *pl = planes + (size_t)p * npix;
     uint32_t wstart = t * TILE + wid * WARP_PIX;
     uint32_t info[WARP_ITERS];  // rank(13) | delta(9) << 13 | oor << 22
     uint16_t ev[WARP_ITERS];
     const uint32_t lt = (1u << lane) - 1u;
+    uint32_t py = (wstart + lane) / w, px = wstart + lane - py * w;
 #pragma unroll
     for (int it = 0; it < WARP_ITERS; it++) {
         uint32_t i = wstart + it * 32 + lane;
         bool oor = false;
         int delta = 0, val = 0;
         if (i >= 2 && i < npix) {
-            PixelClass pc = classify_pixel(pl, i, w);
+            PixelClass pc = classify_pixel_xy(pl, i, px, py, w);
             oor = pc.cls != 0;
             delta = pc.delta;
             val = pc.val;
@@ -189,6 +197,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const int16_t *__restr
         __syncwarp();
         info[it] = rank | ((uint32_t)delta << 13) | (oor ? (1u << 22) : 0u);
         ev[it] = (uint16_t)val;
+        advance_xy(px, py, i + 32, 32, w);
     }
     __syncthreads();
     // exclusive prefix over warps, per context, on top of the tile's base
@@ -602,23 +611,25 @@ __global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, c
 // ------------------------------------------------------------------------------------
 // code: marker + code word per pixel (compression.rs:130-145), bits per tile
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE_THREADS) k_code(const int16_t *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp,
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS) k_code(const T *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp,
                                                        uint32_t cap, const uint32_t *__restrict__ gidx,
                                                        const uint8_t *__restrict__ k_grp, uint32_t *__restrict__ rec,
                                                        uint32_t *__restrict__ tile_bits) {
     __shared__ uint32_t wsum[TILE_WARPS];
     uint32_t bid = blockIdx.x;
     uint32_t p = bid / tpp, t = bid - p * tpp;
-    const int16_t *pl = planes + (size_t)p * npix;
+    const T *pl = planes + (size_t)p * npix;
     uint32_t start = t * TILE;
     uint32_t bits = 0;
+    uint32_t i = start + threadIdx.x;
+    uint32_t y = i / w, x = i - y * w;
 #pragma unroll 4
-    for (int j = 0; j < TILE / TILE_THREADS; j++) {
-        uint32_t i = start + j * TILE_THREADS + threadIdx.x;
+    for (int j = 0; j < TILE / TILE_THREADS; j++, i += TILE_THREADS) {
         if (i >= npix) break;
         uint32_t r = 0;
         if (i >= 2) {
-            PixelClass pc = classify_pixel(pl, i, w);
+            PixelClass pc = classify_pixel_xy(pl, i, x, y, w);
             if (pc.cls == 0) {
                 int len;
                 uint32_t code = phase_in_code((uint32_t)pc.delta + 1u, (uint32_t)pc.val, len);
@@ -642,6 +653,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code(const int16_t *__restrict
         }
         rec[(size_t)p * npix + i] = r;
         bits += rec_len(r);
+        advance_xy(x, y, i + TILE_THREADS, TILE_THREADS, w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
@@ -841,7 +853,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_pack(PackArgs a) {
 }
 
 // header + raw first two samples of every plane (format.rs:51-61, compression.rs:93-108)
-__global__ void k_heads(PackArgs a, const int16_t *__restrict__ planes, uint32_t np, uint32_t width, uint32_t height,
+template <typename T>
+__global__ void k_heads(PackArgs a, const T *__restrict__ planes, uint32_t np, uint32_t width, uint32_t height,
                         uint32_t color, uint32_t depth) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= np) return;
@@ -906,7 +919,7 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
     Layout L;
     Carver c{base};
     size_t np = ni * g.nch;
-    L.planes = c.take<int16_t>(np * g.npix + 8);
+    L.planes = c.take<int16_t>(g.nch == 1 ? 8 : np * g.npix + 8);   // gray needs no planes
     L.tile_hist = c.take<uint32_t>(np * g.tpp * NBIN);
     L.chunk_tot = c.take<uint32_t>(np * g.nchunks * NBIN);
     L.chain_count = c.take<uint32_t>(np * NBIN);
@@ -1004,12 +1017,13 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
         L = carve((uint8_t *)ctx->scratch, g, ni);
         const uint8_t *px = (const uint8_t *)d_pixels + first * img_pix_bytes;
 
-        if (g.npix > 0) {
+        // gray samples are classified straight from the caller's pixels; RGB goes through Y/Co/Cg planes
+        const bool gray = g.nch == 1;
+        if (g.npix > 0 && !gray) {
             StageScope s(ctx, ST_PLANES);
             size_t total = ni * (size_t)g.npix;
             unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
-            if (g.nch == 1) k_to_planes_gray8<<<blocks, 256, 0, st>>>(px, L.planes, total);
-            else k_to_planes_rgb8<<<blocks, 256, 0, st>>>(px, L.planes, g.npix, total);
+            k_to_planes_rgb8<<<blocks, 256, 0, st>>>(px, L.planes, g.npix, total);
             s.launched();
         }
         const unsigned ntiles = (unsigned)(np * g.tpp);
@@ -1018,7 +1032,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 StageScope s(ctx, ST_HIST);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.chunk_tot, 0, np * g.nchunks * NBIN * sizeof(uint32_t), st));
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.counters, 0, 8 * sizeof(uint32_t), st));
-                k_hist<<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                if (gray) k_hist<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                else k_hist<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
                 s.launched();
             }
             {
@@ -1034,7 +1049,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_SCATTER);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.e_grp, 0xFF, np * (size_t)g.cap * sizeof(uint16_t), st));
-                k_scatter<<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
+                if (gray) k_scatter<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
+                else k_scatter<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
                 s.launched();
             }
             const unsigned ngroups = (unsigned)(np * g.gpp);
@@ -1105,7 +1121,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             }
             {
                 StageScope s(ctx, ST_CODE);
-                k_code<<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
+                if (gray) k_code<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
+                else k_code<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
                 s.launched();
             }
         } else if (ntiles) {
@@ -1163,7 +1180,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_pack<<<ntiles, TILE_THREADS, 0, st>>>(pa);
                 s.launched();
             }
-            k_heads<<<(unsigned)((np + 127) / 128), 128, 0, st>>>(pa, L.planes, (uint32_t)np, g.w, g.h, hdr.color_type, hdr.pixel_depth);
+            if (gray) k_heads<uint8_t><<<(unsigned)((np + 127) / 128), 128, 0, st>>>(pa, px, (uint32_t)np, g.w, g.h, hdr.color_type, hdr.pixel_depth);
+            else k_heads<int16_t><<<(unsigned)((np + 127) / 128), 128, 0, st>>>(pa, L.planes, (uint32_t)np, g.w, g.h, hdr.color_type, hdr.pixel_depth);
             s.launched();
         }
         if (!d_arena) {
