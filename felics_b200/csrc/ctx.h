@@ -92,6 +92,9 @@ int profile_collect(felics_ctx *ctx);  // after a stream sync: fold pending even
 // encode.cu
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                         uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
+// encode16.cu: 16-bit samples
+int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
+                          uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
 // decode.cu
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host);

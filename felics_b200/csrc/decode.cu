@@ -8,6 +8,7 @@
 // table (511 contexts x 6 counters, parameter_selection.rs:29-33) in shared memory.
 #include "ctx.h"
 #include "device_common.cuh"
+#include "serial16.cuh"
 
 #include <algorithm>
 
@@ -425,12 +426,190 @@ __global__ void k_unplane_rgb8(const int16_t *__restrict__ planes, uint8_t *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 16-bit samples: the reference loop as written, one warp per file (serial16.cuh)
+// ---------------------------------------------------------------------------------------------
+struct Dec16Args {
+    const uint32_t *words;
+    uint64_t arena_words;
+    const uint64_t *offsets;
+    int32_t *planes;           // [n*nch][npix]
+    uint32_t *tables;          // [n][TABLE16_WORDS]
+    int *status;
+    uint32_t w, h, npix, nch;
+    uint8_t color, depth;
+};
+
+__global__ void __launch_bounds__(32) k16_decode(Dec16Args a, uint32_t n) {
+    const uint32_t img = blockIdx.x;
+    if (img >= n) return;
+    const uint32_t lane = threadIdx.x;
+    const uint64_t off0 = a.offsets[img], off1 = a.offsets[img + 1];
+    const uint64_t len = off1 - off0;
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(a.words);
+    int st = FELICS_OK;
+    if (lane == 0) {   // read_header order (format.rs:63-84), then decompress_with_header's checks
+        const uint8_t *hb = bytes + off0;
+        if (len < 4) st = FELICS_ERR_IO;
+        else if (hb[0] != 'F' || hb[1] != 'L' || hb[2] != 'C' || hb[3] != 'S') st = FELICS_ERR_INVALID_SIGNATURE;
+        else if (len < 5) st = FELICS_ERR_IO;
+        else if (hb[4] > 1) st = FELICS_ERR_INVALID_COLOR_TYPE;
+        else if (len < 6) st = FELICS_ERR_IO;
+        else if (hb[5] > 1) st = FELICS_ERR_INVALID_PIXEL_DEPTH;
+        else if (len < FELICS_HEADER_BYTES) st = FELICS_ERR_IO;
+        else if (hb[4] != a.color) st = FELICS_ERR_INVALID_COLOR_TYPE;
+        else if (hb[5] != a.depth) st = FELICS_ERR_INVALID_PIXEL_DEPTH;
+        else {
+            uint32_t w = ((uint32_t)hb[6] << 24) | ((uint32_t)hb[7] << 16) | ((uint32_t)hb[8] << 8) | hb[9];
+            uint32_t h = ((uint32_t)hb[10] << 24) | ((uint32_t)hb[11] << 16) | ((uint32_t)hb[12] << 8) | hb[13];
+            if (w != a.w || h != a.h) st = FELICS_ERR_INVALID_DIMENSIONS;
+        }
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st != FELICS_OK) { if (lane == 0) a.status[img] = st; return; }
+
+    BitReader br;
+    br.init(a.words, a.arena_words, 8 * (off0 + FELICS_HEADER_BYTES), 8 * off1);
+    uint32_t *tab = a.tables + (size_t)img * TABLE16_WORDS;
+    const uint32_t w = a.w;
+    for (uint32_t ch = 0; ch < a.nch && st == FELICS_OK; ch++) {
+        clear_table16(tab, lane);
+        if (lane == 0) {
+            int32_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.npix;
+            const int32_t p1 = (int32_t)br.read(32), p2 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
+            if (br.eof) st = FELICS_ERR_IO;
+            else {
+                if (a.npix >= 1) pl[0] = p1;
+                if (a.npix >= 2) pl[1] = p2;
+            }
+            uint32_t x = 0, y = 0;
+            if (a.npix >= 3) { y = 2 / w; x = 2 - y * w; }
+            for (uint32_t i = 2; i < a.npix && st == FELICS_OK; i++) {
+                uint32_t ia, ib;
+                neighbours16(i, x, y, w, ia, ib);
+                const long long v1 = pl[ia], v2 = pl[ib];
+                const long long hi = max(v1, v2), lo = min(v1, v2);
+                if (hi - lo > (long long)MAXCTX16) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
+                const uint32_t ctx = (uint32_t)(hi - lo);
+                uint32_t *row = tab + (size_t)ctx * ROW16;
+                long long value;
+                if (br.read(1)) {                                       // InRange (:208-215)
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    const uint32_t nn = ctx + 1;
+                    const int m = 31 - __clz(nn);
+                    const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                    uint32_t xx = br.read((uint32_t)m);
+                    if (xx >= right_p) xx = (xx - right_p) * 2 + right_p + br.read(1);   // phase_in_coding.rs:102-109
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    xx += left_p;                                                        // rotate_left (:55-57)
+                    if (xx >= nn) xx -= nn;
+                    if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
+                    value = lo + (long long)xx;
+                } else {
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    const uint32_t above = br.read(1);
+                    const int k = get_k16(row);                            // get_k (:202)
+                    const uint32_t q = br.read_unary0();
+                    const uint32_t rem = br.read((uint32_t)k);
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    if (q > (1u << 20)) { st = FELICS_ERR_INVALID_VALUE; break; }
+                    const uint32_t e = (q << k) + rem;
+                    update16(row, e);
+                    value = above ? hi + (long long)e + 1 : lo - (long long)e - 1;   // (:216-243)
+                }
+                if (value < -2147483648ll || value > 2147483647ll) { st = FELICS_ERR_VALUE_OVERFLOW; break; }   // checked_add / checked_sub
+                pl[i] = (int32_t)value;
+                if (++x == w) { x = 0; y++; }
+            }
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+    }
+    if (lane == 0) a.status[img] = st;
+}
+
+// i32 planes -> u16 pixels with the try_into range checks (compression.rs:305-310, :402-407)
+__global__ void k16_unplane_gray(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t total, int *__restrict__ status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const size_t img = i / npix;
+        if (status[img] != FELICS_OK) continue;
+        const int v = planes[i];
+        if (v < 0 || v > 65535) { atomicCAS(&status[img], FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
+        px[i] = (uint16_t)v;
+    }
+}
+__global__ void k16_unplane_rgb(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t total, int *__restrict__ status) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; idx < total; idx += stride) {
+        const size_t img = idx / npix;
+        if (status[img] != FELICS_OK) continue;
+        const uint32_t i = (uint32_t)(idx - img * npix);
+        const int32_t *base = planes + img * 3 * (size_t)npix;
+        const long long y = base[i], co = base[(size_t)npix + i], cg = base[2 * (size_t)npix + i];
+        const long long t = y - cg / 2;      // color_transform.rs:20-26
+        const long long g = cg + t;
+        const long long b = t - co / 2;
+        const long long r = b + co;
+        if (r < 0 || r > 65535 || g < 0 || g > 65535 || b < 0 || b > 65535) { atomicCAS(&status[img], FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
+        px[3 * idx] = (uint16_t)r; px[3 * idx + 1] = (uint16_t)g; px[3 * idx + 2] = (uint16_t)b;
+    }
+}
+
+static int decode16_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host, const felics_header &hdr,
+                                 void *d_pixels_out, int *status_host) {
+    const uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
+    cudaStream_t st = ctx->stream;
+    const uint32_t npix = (uint32_t)npix64, nch = hdr.color_type ? 3 : 1;
+    const size_t sub = std::max<size_t>(1, std::min<size_t>(n, 64));
+    size_t off_bytes = align_up((n + 1) * sizeof(uint64_t), 256);
+    size_t stat_bytes = align_up(n * sizeof(int), 256);
+    size_t plane_bytes = align_up((sub * nch * (size_t)npix + 8) * sizeof(int32_t), 256);
+    size_t table_bytes = align_up(sub * TABLE16_WORDS * sizeof(uint32_t), 256);
+    int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off_bytes + stat_bytes + plane_bytes + table_bytes);
+    if (rc) return rc;
+    uint8_t *sb = (uint8_t *)ctx->scratch;
+    uint64_t *d_off = (uint64_t *)sb;
+    int *d_status = (int *)(sb + off_bytes);
+    int32_t *d_planes = (int32_t *)(sb + off_bytes + stat_bytes);
+    uint32_t *d_tables = (uint32_t *)(sb + off_bytes + stat_bytes + plane_bytes);
+    FELICS_CUDA_TRY(cudaMemcpyAsync(d_off, offsets_host, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    const size_t img_bytes = (size_t)npix * nch * 2;
+    for (size_t first = 0; first < n; first += sub) {
+        const size_t ni = std::min(sub, n - first);
+        Dec16Args a;
+        a.words = (const uint32_t *)d_arena;
+        a.arena_words = (offsets_host[n] + 3) / 4;
+        a.offsets = d_off + first; a.planes = d_planes; a.tables = d_tables; a.status = d_status + first;
+        a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch; a.color = hdr.color_type; a.depth = hdr.pixel_depth;
+        {
+            StageScope s(ctx, ST_DECODE);
+            k16_decode<<<(unsigned)ni, 32, 0, st>>>(a, (uint32_t)ni);
+            s.launched();
+        }
+        if (npix > 0) {
+            StageScope s(ctx, ST_UNPLANE);
+            const size_t total = ni * (size_t)npix;
+            const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
+            uint16_t *out = (uint16_t *)((uint8_t *)d_pixels_out + first * img_bytes);
+            if (nch == 1) k16_unplane_gray<<<blocks, 256, 0, st>>>(d_planes, out, npix, total, d_status + first);
+            else k16_unplane_rgb<<<blocks, 256, 0, st>>>(d_planes, out, npix, total, d_status + first);
+            s.launched();
+        }
+    }
+    FELICS_CUDA_TRY(cudaMemcpyAsync(status_host, d_status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+    FELICS_CUDA_TRY(cudaGetLastError());
+    rc = profile_collect(ctx);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (status_host[i] != FELICS_OK) return status_host[i];
+    return FELICS_OK;
+}
+
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host) {
-    if (hdr.pixel_depth != 0) {
-        set_error("16-bit samples are not built yet (traits.rs:35-43 is a 'next' row)");
-        return FELICS_ERR_UNSUPPORTED;
-    }
     if (((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;
@@ -438,6 +617,7 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
     if (npix64 > 0xffffffffull) return FELICS_ERR_INVALID_DIMENSIONS;   // checked_mul, compression.rs:176-180
     if (npix64 > 0x7fff0000ull) { set_error("image too large for one call"); return FELICS_ERR_INVALID_DIMENSIONS; }
+    if (hdr.pixel_depth != 0) return decode16_batch_device(ctx, n, d_arena, offsets_host, hdr, d_pixels_out, status_host);
     cudaStream_t st = ctx->stream;
     const uint32_t npix = (uint32_t)npix64;
     const uint32_t nch = hdr.color_type ? 3 : 1;

@@ -971,10 +971,7 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
 // With h_arena every sub-batch is packed into the context's staging buffer and copied out.
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena,
                         uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host) {
-    if (hdr.pixel_depth != 0) {
-        set_error("16-bit samples are not built yet (traits.rs:35-43 is a 'next' row)");
-        return FELICS_ERR_UNSUPPORTED;
-    }
+    if (hdr.pixel_depth != 0) return encode16_batch_device(ctx, n, d_pixels, hdr, d_arena, h_arena, arena_cap, offsets_host);
     if (d_arena && ((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;

@@ -207,3 +207,50 @@ def test_long_chains(codec):
     yy, xx = np.mgrid[0:900, 0:1400]
     check(codec, np.clip(90 + ((xx * 3 + yy) // 11) % 60 + rng.integers(-1, 2, xx.shape), 0, 255).astype(np.uint8))
     check(codec, np.clip(128 + rng.normal(0, 1.2, (1100, 1000)), 0, 255).astype(np.uint8))  # near-tied counters
+
+
+# ---- 16-bit samples (traits.rs:35-43): K = {0..14}, contexts up to 131070 --------------------
+def test_gray16_golden_crop(codec, golden_images):
+    check(codec, golden_images["gray16_crop"])
+
+
+@pytest.mark.parametrize("width,height", [(2, 1), (1, 2), (1, 1), (4, 7), (100, 40), (124, 74), (44, 1), (1, 100)])
+def test_compression_decompression_16bit(codec, width, height):  # compression.rs:500-530 (u16 half)
+    rng = np.random.default_rng(width * 77 + height)
+    check(codec, rng.integers(0, 65536, (height, width), dtype=np.uint16))
+    check(codec, rng.integers(0, 65536, (height, width, 3), dtype=np.uint16))
+
+
+def test_16bit_structure_and_extremes(codec):
+    rng = np.random.default_rng(9)
+    yy, xx = np.mgrid[0:120, 0:200]
+    smooth = np.clip(30000 + 9000 * np.sin(xx / 23.0) * np.cos(yy / 17.0) + rng.normal(0, 40, xx.shape), 0, 65535).astype(np.uint16)
+    check(codec, smooth)
+    check(codec, np.stack([smooth, np.roll(smooth, 3, 1), smooth[::-1]], axis=-1).copy())
+    check(codec, (((xx + yy) & 1) * 65535).astype(np.uint16))          # residuals of 65534 with k = 14 .. 0: very long unary runs
+    check(codec, np.full((30, 50), 65535, np.uint16))
+    check(codec, np.zeros((3, 0), np.uint16))
+    z = np.zeros((20, 30, 3), np.uint16)
+    z[::2, ::3, 0] = 65535
+    z[1::2, ::2, 2] = 65535
+    check(codec, z)                                                     # Co/Cg of +-65535
+
+
+def test_batch_16bit(codec):
+    rng = np.random.default_rng(4)
+    imgs = rng.integers(0, 65536, (3, 40, 60), dtype=np.uint16)
+    imgs[1] >>= 6
+    arena, offsets = codec.compress_batch(imgs)
+    for i, img in enumerate(imgs):
+        assert arena[int(offsets[i]):int(offsets[i + 1])].tobytes() == fo.compress(img), f"image {i}"
+    hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Sixteen, 60, 40)
+    out, status = codec.decompress_batch(arena, offsets, hdr)
+    assert not status.any() and np.array_equal(out, imgs)
+
+
+def test_16bit_truncated(codec):
+    img = np.random.default_rng(1).integers(0, 65536, (20, 30), dtype=np.uint16)
+    fel = codec.compress(img)
+    with pytest.raises(felics_b200.DecompressionError) as e:
+        codec.decompress(fel[: len(fel) // 2])
+    assert e.value.kind == "IoError"
