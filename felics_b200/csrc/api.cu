@@ -42,7 +42,7 @@ int ensure_buffer(felics_ctx *ctx, void **buf, size_t *cap, size_t need, bool pi
     return FELICS_OK;
 }
 
-StageScope::StageScope(felics_ctx *c, int st) : ctx(c), stage(st) {
+StageScope::StageScope(felics_ctx *c, int st, cudaStream_t stream) : ctx(c), stage(st), on(stream ? stream : c->stream) {
     if (!ctx->prof) return;
     auto take = [&]() {
         cudaEvent_t e = nullptr;
@@ -51,16 +51,16 @@ StageScope::StageScope(felics_ctx *c, int st) : ctx(c), stage(st) {
         return e;
     };
     a = take(); b = take();
-    cudaEventRecord(a, ctx->stream);
+    cudaEventRecord(a, on);
 }
 StageScope::~StageScope() {
     static const bool sync_each = getenv("FELICS_B200_SYNC") != nullptr;   // debug: localise a faulting stage
     if (sync_each) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(on);
         if (e != cudaSuccess) fprintf(stderr, "felics_b200: stage %d failed: %s\n", stage, cudaGetErrorString(e));
     }
     if (!a) return;
-    cudaEventRecord(b, ctx->stream);
+    cudaEventRecord(b, on);
     ctx->prof_pending.push_back({stage, a, b});
 }
 
@@ -134,6 +134,9 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->staging_in) cudaFree(ctx->staging_in);
     if (ctx->staging_out) cudaFree(ctx->staging_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

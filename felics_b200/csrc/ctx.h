@@ -40,6 +40,8 @@ struct felics_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;      // second stream: the serial epoch walk runs beside the speculative one
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     void *scratch = nullptr;      // device scratch, grown on demand
     size_t scratch_cap = 0;
@@ -83,7 +85,8 @@ struct StageScope {
     felics_ctx *ctx;
     int stage;
     cudaEvent_t a = nullptr, b = nullptr;
-    StageScope(felics_ctx *c, int st);
+    cudaStream_t on;
+    StageScope(felics_ctx *c, int st, cudaStream_t stream = nullptr);
     ~StageScope();
     void launched(int n = 1) { ctx->stage_launches[stage] += n; ctx->total_launches += n; }
 };

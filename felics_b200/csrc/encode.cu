@@ -502,16 +502,22 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + w * 32u) * 4, nb * 64u, &bars[buf]);
             }
         };
-        for (uint32_t w = 0; w < min(nwin, (uint32_t)WALK_BUF - 1u); w++) prefetch(w);
+        uint32_t issued = min(nwin, (uint32_t)WALK_BUF - 1u);   // windows whose copy has been started
+        for (uint32_t w = 0; w < issued; w++) prefetch(w);
+        bool aborted = false;   // the speculative walk (running beside this kernel) resolved the chain
+        uint32_t flag = 0;      // resolved[pc], polled one window ahead so that the load never stalls the walk
 
         uint32_t nep = 1;       // epochs recorded so far
         uint32_t cur = 0;       // chain-relative first element of the current epoch
         bool overflow = false;
-        for (uint32_t w = 0; w < nwin; w++) {
+        for (uint32_t w = 0; w < issued; w++) {
             const uint32_t buf = w % WALK_BUF;
-            if (w + WALK_BUF - 1 < nwin) prefetch(w + WALK_BUF - 1);   // its buffer was consumed in the previous iteration
+            if (flag == 1) aborted = true;
+            if (a.resolved && (w & 31u) == 0) flag = *reinterpret_cast<const volatile uint8_t *>(a.resolved + pc);
+            if (!aborted && issued < nwin) { prefetch(issued); issued++; }   // its buffer was consumed in the previous iteration
             mbar_wait(&bars[buf], (phases >> buf) & 1u);
             phases ^= 1u << buf;
+            if (aborted) continue;                                          // only drain the copies in flight
             const uint4 *wf = &sfine[buf][0];
             const uint4 *wb = &sblk[buf][0];
             const uint32_t wblk0 = w * 32u;
@@ -564,7 +570,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             if (valid) a.blk_epoch[blk0 + wblk0 + lane] = ep0 + my_epoch;
             __syncwarp();
         }
-        if (lane == 0) {
+        if (lane == 0 && !aborted) {
             if (overflow) atomicOr(&a.counters[2], 1u);
             else rec[2 * nep + 1] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // sentinel
         }
@@ -1067,6 +1073,47 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 s.launched(3);
             }
             FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_resolved, 0, np * NBIN, st));
+            // With the speculative walk on, the serial walker starts at the same time on a second stream: it walks
+            // every chain and drops a chain as soon as the speculation has resolved it (both write identical
+            // records), so the speculation's latency is hidden behind the chains that must be walked serially.
+            const bool overlap = L.sp && !ctx->no_spec;
+            cudaStream_t wst = st;
+            if (overlap) {
+                if (!ctx->side) {
+                    FELICS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+                    FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+                    FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+                }
+                wst = ctx->side;
+                FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_fork, st));
+                FELICS_CUDA_TRY(cudaStreamWaitEvent(wst, ctx->ev_fork, 0));
+            }
+            auto launch_walk = [&]() -> int {
+                StageScope s(ctx, ST_WALK, wst);
+                WalkArgs wa;
+                wa.resolved = L.sp_resolved;
+                wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
+                wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
+                wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
+                wa.cap = g.cap; wa.epcap = g.epcap;
+                // beside the speculative kernels every walker warp gets a whole SM (its shared-memory request leaves no room
+                // for other blocks): the walk is a latency chain, co-resident blocks would steal its issue slots
+                const size_t walk_smem = overlap ? (size_t)200 * 1024 : sizeof(WalkSmem);
+                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, overlap ? 148 : 148 * 3);
+                static bool walk_attr_done = false;
+                if (!walk_attr_done) {
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    walk_attr_done = true;
+                }
+                k_walk<<<blocks, 32, walk_smem, wst>>>(wa);
+                s.launched();
+                return FELICS_OK;
+            };
+            if (overlap) {
+                int wrc = launch_walk();
+                if (wrc) return wrc;
+                FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_join, wst));
+            }
             if (L.sp && !ctx->no_spec) {
                 StageScope s(ctx, ST_SPEC);
                 SpArgs sa;
@@ -1088,26 +1135,16 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_scan<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
                 k_sp_emit<<<(z.max_seg + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_blocksum<<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
-                k_sp_finish<<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
+                k_sp_finish<false><<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
+                k_sp_finish<true><<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
-                s.launched(8);
+                s.launched(9);
             }
-            {
-                StageScope s(ctx, ST_WALK);
-                WalkArgs wa;
-                wa.resolved = L.sp_resolved;
-                wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
-                wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
-                wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
-                wa.cap = g.cap; wa.epcap = g.epcap;
-                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 3);
-                static bool walk_attr_done = false;
-                if (!walk_attr_done) {
-                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)));
-                    walk_attr_done = true;
-                }
-                k_walk<<<blocks, 32, sizeof(WalkSmem), st>>>(wa);
-                s.launched();
+            if (overlap) {
+                FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+            } else {
+                int wrc = launch_walk();
+                if (wrc) return wrc;
             }
             {
                 StageScope s(ctx, ST_KFILL);

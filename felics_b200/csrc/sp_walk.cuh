@@ -376,13 +376,16 @@ __device__ __forceinline__ uint32_t sp_block_start(const unsigned long long *__r
     return (uint32_t)S;
 }
 
-// 6. per block of 32 epochs: exact counters at every epoch start, verification, epoch records, block epochs
+// 6. per block of 32 epochs: exact counters at every epoch start.  WRITE = false: verification only (any failing epoch
+//    rejects the chain); WRITE = true, after every block has been verified: epoch records and block epochs of the accepted
+//    chains.  Rejected chains are never written, so the serial walker may run beside this kernel.
+template <bool WRITE>
 __global__ void __launch_bounds__(128) k_sp_finish(SpArgs a) {
     const uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
     if (slot >= a.counts[3]) return;
     const uint32_t di = a.eb_desc[slot];
     const uint32_t fail = a.chain_fail[di];
-    if (fail != SP_OK && fail != SP_OK - 1) return;   // rejected before this kernel
+    if (WRITE ? fail != SP_OK : (fail != SP_OK && fail != SP_OK - 1)) return;   // rejected
     const SpDesc d = a.desc[di];
     const uint32_t n = a.chain_n[di];
     const uint32_t b = slot - d.eb0;
@@ -447,7 +450,10 @@ __global__ void __launch_bounds__(128) k_sp_finish(SpArgs a) {
         // open last epoch: no halving may be left (kb <= 1024 after the last element)
         if ((int32_t)vkb > (int32_t)HALVE_AT) bad = true;
     }
-    if (bad) atomicMin(&a.chain_fail[di], SP_OK - 1);   // any failure rejects the chain
+    if (!WRITE) {
+        if (bad) atomicMin(&a.chain_fail[di], SP_OK - 1);   // any failure rejects the chain
+        return;
+    }
     if (has_epoch) {
         uint4 *rec = a.ep_rec + (size_t)(d.ep0 + e) * 2;
         rec[0] = make_uint4(S[0] - T0[0], S[1] - T0[1], S[2] - T0[2], S[3] - T0[3]);
