@@ -157,6 +157,11 @@ def run_reference(args):
         imgs = [tile_batch(per, first=r * args.tiles) for r in range(n)]
         sample = f"{per} of {args.tiles} 512x512 tiles per replica, {n} replica(s), one image per thread"
         px_per_step = per * TILE_W * TILE_H * n
+    elif args.workload == "rgb":
+        rows = 1024  # bounded sample: the top 1024 rows of each replica's frame (7.9 MPixel, 23.6 MSample)
+        imgs = [gnat_rgb(W3, rows, rank=r) for r in range(n)]
+        sample = f"top {rows} rows (7680x{rows}) of each replica's 7680x4320 RGB frame, {n} replica(s), one image per thread"
+        px_per_step = W3 * rows * n
     else:
         rows = 2048  # bounded sample: the top 2048 rows of each replica's image (16.8 MPixel)
         imgs = [gnat_image(W2, rows, seed=2 + r) for r in range(n)]
@@ -197,7 +202,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gnat_rgb(width, height, rank=0):
+    """three G-nat planes, phases (0, 11, 23) px, seeds 3, 4, 5 (+3*rank), interleaved R, G, B."""
+    return np.stack([gnat_image(width, height, seed=s + 3 * rank, phase=p) for s, p in ((3, 0), (4, 11), (5, 23))], axis=-1)
+
+
+W3, H3 = 7680, 4320
+
+
 def workload_name(args):
+    if args.workload == "rgb":
+        return "configs[2]: one synthetic 7680x4320 8-bit RGB frame (three G-nat planes, YCoCg-R inside the timed path) per GPU, encode"
     if args.workload == "tiles":
         return f"configs[3]-style: {args.tiles} synthetic 512x512 gray8 tiles per GPU (integer generator, seed 1), encode"
     return "configs[1]: one synthetic 8192x8192 gray8 image (G-nat, seed 2+rank) per GPU, encode"
@@ -227,14 +242,19 @@ def run_ours(args):
         chunk = 256
         host = np.concatenate([tile_batch(min(chunk, n_img - s), first=rank * n_img + s) for s in range(0, n_img, chunk)])
         hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, TILE_W, TILE_H)
+    elif args.workload == "rgb":
+        n_img = 1
+        host = gnat_rgb(W3, H3, rank=rank)[None]
+        hdr = felics_b200.Header(felics_b200.ColorType.Rgb, felics_b200.PixelDepth.Eight, W3, H3)
     else:
         n_img = 1
         host = gnat_image(W2, H2, seed=2 + rank)[None]
         hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, W2, H2)
-    pixels = int(host.size)
+    samples = int(host.size)                                   # bytes in = samples (u8)
+    pixels = samples // (3 if args.workload == "rgb" else 1)   # an RGB pixel is one pixel, three samples
     pin_in = torch.from_numpy(host).pin_memory()
     d_in = pin_in.to(dev, non_blocking=True)
-    cap = pixels + pixels // 2 + 4096 * n_img
+    cap = samples + samples // 2 + 4096 * n_img
     d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
     pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -301,7 +321,7 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # decode (reported, not the target): the same .fel decoded on the GPU, timed once per step budget
-    d_pix_out = torch.empty(pixels, dtype=torch.uint8, device=dev)
+    d_pix_out = torch.empty(samples, dtype=torch.uint8, device=dev)
     dec_steps = 1 if args.workload != "tiles" else min(args.steps, 3)
     codec.profile(True)
     t0 = time.perf_counter()
@@ -335,7 +355,7 @@ def run_ours(args):
         enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane")}
         dom = max(enc_stages, key=lambda k: enc_stages[k][0])
         dom_ms, dom_launches = enc_stages[dom]
-        alg_bytes = pixels + fel_bytes          # S*b + C, per launch: one launch covers the whole batch
+        alg_bytes = samples + fel_bytes         # S*b + C, per launch: one launch covers the whole batch
         dom_avg_ms = dom_ms / max(dom_launches, 1)
         achieved = alg_bytes / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
         whole_achieved = alg_bytes * args.steps / (sum(ms_dev) * 1e-3) / 1e9
@@ -351,6 +371,15 @@ def run_ours(args):
             sample = "first 64 tiles of rank 0's batch, 1 thread"
             want = fo.compress(host[0])
             got = d_out[: int(offsets[1])].cpu().numpy().tobytes()
+        elif args.workload == "rgb":
+            rows = 1024
+            t0 = time.perf_counter()
+            fo.compress(host[0][:rows])
+            cpu_s = time.perf_counter() - t0
+            cpu_px = W3 * rows
+            sample = f"top {rows} rows of rank 0's frame (7680x{rows} RGB), 1 thread (a single image is serial in the reference)"
+            want = None
+            got = d_out[:fel_bytes].cpu().numpy().tobytes()
         else:
             rows = 2048
             t0 = time.perf_counter()
@@ -373,13 +402,14 @@ def run_ours(args):
             "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(args), "l2": "flushed between timed steps (256 MiB device write); each step timed with CUDA events on the launching stream",
-                       "fel_bytes_rank0": fel_bytes, "bits_per_pixel": 8.0 * fel_bytes / pixels},
+                       "fel_bytes_rank0": fel_bytes, "bits_per_sample": 8.0 * fel_bytes / samples,
+                       "msample_per_s": value * samples / pixels},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(dom), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": dom_avg_ms,
                          "whole_encode_achieved_gbs": whole_achieved, "whole_encode_frac": whole_achieved / peak},
             "cpu_baseline": {"value": cpu_px / cpu_s / 1e6, "unit": "MPixel/s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": pixels, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
+            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": samples, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
                     "ms_per_step": tot_e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -401,7 +431,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["image", "tiles"], default="image")
+    ap.add_argument("--workload", choices=["image", "rgb", "tiles"], default="image")
     ap.add_argument("--tiles", type=int, default=2048, help="tiles per GPU for --workload tiles")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check of the timed output")
     ap.add_argument("--no-decode", dest="decode", action="store_false", help="skip the (slow, single-stream) decode measurement")

@@ -235,6 +235,29 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const T *__restrict__ 
 // ------------------------------------------------------------------------------------
 constexpr int BLK_REC = 16;
 
+// code costs (e >> k) + 1 + k of one residual for k = 0..5, two 16-bit lanes per word; padding slots cost nothing
+__device__ __forceinline__ void pack_costs(uint32_t e, uint32_t &u01, uint32_t &u23, uint32_t &u45) {
+    u01 = u23 = u45 = 0;
+    if (e != PAD_E) {
+        u01 = (e + 1u) | (((e >> 1) + 2u) << 16);
+        u23 = ((e >> 2) + 3u) | (((e >> 3) + 4u) << 16);
+        u45 = ((e >> 4) + 5u) | (((e >> 5) + 6u) << 16);
+    }
+}
+// inclusive scan over the 32 lanes of a warp (= one 32-block of grouped elements)
+__device__ __forceinline__ void warp_scan3(uint32_t &u01, uint32_t &u23, uint32_t &u45, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t a = __shfl_up_sync(0xffffffffu, u01, o);
+        uint32_t b = __shfl_up_sync(0xffffffffu, u23, o);
+        uint32_t c = __shfl_up_sync(0xffffffffu, u45, o);
+        if (lane >= (uint32_t)o) { u01 += a; u23 += b; u45 += c; }
+    }
+}
+
+// FINE = true: the per-element records are written (big single images: the speculative walk and the latency-bound
+// serial walk read them); FINE = false: only block records, the consumers redo the 32-element scan themselves.
+template <bool FINE>
 __global__ void __launch_bounds__(GROUP) k_prefix(const uint16_t *__restrict__ e_grp, uint32_t cap, uint32_t gpp,
                                                   const uint32_t *__restrict__ plane_used, uint4 *__restrict__ fine,
                                                   uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ grp_tot) {
@@ -246,20 +269,10 @@ __global__ void __launch_bounds__(GROUP) k_prefix(const uint16_t *__restrict__ e
     size_t g = (size_t)p * cap + off + threadIdx.x;
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t e = e_grp[g];
-    uint32_t u01 = 0, u23 = 0, u45 = 0;
-    if (e != PAD_E) {
-        u01 = (e + 1u) | (((e >> 1) + 2u) << 16);
-        u23 = ((e >> 2) + 3u) | (((e >> 3) + 4u) << 16);
-        u45 = ((e >> 4) + 5u) | (((e >> 5) + 6u) << 16);
-    }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t a = __shfl_up_sync(0xffffffffu, u01, o);
-        uint32_t b = __shfl_up_sync(0xffffffffu, u23, o);
-        uint32_t c = __shfl_up_sync(0xffffffffu, u45, o);
-        if (lane >= (uint32_t)o) { u01 += a; u23 += b; u45 += c; }
-    }
-    fine[g] = make_uint4(u01, u23, u45, e);
+    uint32_t u01, u23, u45;
+    pack_costs(e, u01, u23, u45);
+    warp_scan3(u01, u23, u45, lane);
+    if (FINE) fine[g] = make_uint4(u01, u23, u45, e);
     if (lane == 31) {
         tot[wid][0] = u01 & 0xffffu; tot[wid][1] = u01 >> 16;
         tot[wid][2] = u23 & 0xffffu; tot[wid][3] = u23 >> 16;
@@ -387,7 +400,8 @@ __global__ void __launch_bounds__(256) k_blkfinal(uint4 *__restrict__ blk_rec4, 
 // are prefetched into shared memory with cp.async, double buffered.
 // ------------------------------------------------------------------------------------
 struct WalkArgs {
-    const uint4 *fine;
+    const uint4 *fine;      // per-element prefix records (FINE) ...
+    const uint16_t *e_grp;  // ... or the grouped residuals
     const uint4 *blk_rec4;  // 4 x uint4 per 32-block
     const uint32_t *chain_count;
     const uint32_t *chain_base;
@@ -437,16 +451,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 //                  computed the re-based halved counters for its own element, the winner's are shuffled out
 // No assumption about which counter binds, so the walk is exact for any data.
 constexpr int WALK_BUF = 4;
+template <bool FINE>
 struct WalkSmem {
-    uint4 fine[WALK_BUF][GROUP];
     uint4 blk[WALK_BUF][32 * 4];
     uint64_t bars[WALK_BUF];
+    uint4 fine[FINE ? WALK_BUF : 1][FINE ? GROUP : 1];          // FINE: per-element prefix records
+    uint16_t e[FINE ? 1 : WALK_BUF][FINE ? 8 : GROUP];           // otherwise: the residuals, scanned per block on demand
 };
 
+template <bool FINE>
 __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
     extern __shared__ __align__(128) unsigned char walk_smem[];
-    WalkSmem &WS = *reinterpret_cast<WalkSmem *>(walk_smem);
+    WalkSmem<FINE> &WS = *reinterpret_cast<WalkSmem<FINE> *>(walk_smem);
     auto &sfine = WS.fine;
+    auto &se = WS.e;
     auto &sblk = WS.blk;
     uint64_t *bars = WS.bars;
     const uint32_t lane = threadIdx.x;
@@ -497,8 +515,13 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             if (lane == 0) {
                 const uint32_t buf = w % WALK_BUF;
                 const uint32_t nb = min(nblk - w * 32u, 32u);
-                mbar_expect_tx(&bars[buf], nb * (32u * 16u + 64u));
-                bulk_g2s(&sfine[buf][0], a.fine + gbase + (size_t)w * GROUP, nb * 32u * 16u, &bars[buf]);
+                if (FINE) {
+                    mbar_expect_tx(&bars[buf], nb * (32u * 16u + 64u));
+                    bulk_g2s(&sfine[buf][0], a.fine + gbase + (size_t)w * GROUP, nb * 32u * 16u, &bars[buf]);
+                } else {
+                    mbar_expect_tx(&bars[buf], nb * (32u * 2u + 64u));
+                    bulk_g2s(&se[buf][0], a.e_grp + gbase + (size_t)w * GROUP, nb * 32u * 2u, &bars[buf]);
+                }
                 bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + w * 32u) * 4, nb * 64u, &bars[buf]);
             }
         };
@@ -518,7 +541,8 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             mbar_wait(&bars[buf], (phases >> buf) & 1u);
             phases ^= 1u << buf;
             if (aborted) continue;                                          // only drain the copies in flight
-            const uint4 *wf = &sfine[buf][0];
+            const uint4 *wf = &sfine[FINE ? buf : 0][0];
+            const uint16_t *we = &se[FINE ? 0 : buf][0];
             const uint4 *wb = &sblk[buf][0];
             const uint32_t wblk0 = w * 32u;
             const bool valid = wblk0 + lane < nblk;
@@ -539,7 +563,13 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 if (!m) break;
                 const int B = __ffs(m) - 1;
                 // element level
-                const uint4 f = wf[B * 32 + lane];
+                uint4 f;
+                if (FINE) {
+                    f = wf[B * 32 + lane];
+                } else {
+                    pack_costs(we[B * 32 + lane], f.x, f.y, f.z);
+                    warp_scan3(f.x, f.y, f.z, lane);
+                }
                 const uint4 e0 = wb[B * 4], e1 = wb[B * 4 + 1];
                 uint32_t T[NK], v[NK];
                 T[0] = e0.x + (f.x & 0xffffu); T[1] = e0.y + (f.x >> 16); T[2] = e0.z + (f.y & 0xffffu);
@@ -578,7 +608,8 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
 }
 
 // kfill: one thread per grouped element.
-__global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, const uint4 *__restrict__ blk_rec4,
+template <bool FINE>
+__global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, const uint16_t *__restrict__ e_grp, const uint4 *__restrict__ blk_rec4,
                                                const uint32_t *__restrict__ blk_epoch, const uint4 *__restrict__ ep_rec,
                                                const uint32_t *__restrict__ plane_used, uint32_t cap, uint32_t np,
                                                uint8_t *__restrict__ k_grp) {
@@ -586,8 +617,15 @@ __global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, c
     uint32_t p = (uint32_t)(g / cap);
     if (p >= np) return;
     uint32_t off = (uint32_t)(g - (size_t)p * cap);
-    if (off >= plane_used[p]) return;
-    uint4 f = fine[g];
+    if (off >= plane_used[p]) return;   // whole warps: plane_used and cap are multiples of 32
+    uint4 f;
+    if (FINE) {
+        f = fine[g];
+    } else {
+        f.w = e_grp[g];
+        pack_costs(f.w, f.x, f.y, f.z);
+        warp_scan3(f.x, f.y, f.z, threadIdx.x & 31u);
+    }
     if (f.w == PAD_E) return;
     size_t blk = g >> 5;
     uint32_t ep = blk_epoch[blk];
@@ -935,7 +973,8 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
     L.counters = c.take<uint32_t>(8);
     L.e_grp = c.take<uint16_t>(np * g.cap);
     L.gidx = c.take<uint32_t>(np * g.npix + 8);
-    L.fine = c.take<uint4>(np * g.cap);
+    L.sp = np <= (size_t)SP_MAX_PLANES && g.npix >= SP_MIN_COUNT;   // big single images: speculative walk, per-element records
+    L.fine = c.take<uint4>(L.sp ? np * g.cap : 8);
     L.blk_rec = c.take<uint32_t>(np * (g.cap / 32) * BLK_REC);
     L.grp_tot = c.take<uint32_t>(np * g.gpp * 8 + 8);
     L.super_tot = c.take<uint32_t>((np * g.gpp / 1024 + 2) * 8);
@@ -947,7 +986,6 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
     L.tile_off = c.take<uint64_t>(np * g.tpp + 8);
     L.plane_bits = c.take<uint64_t>(np + 8);
     L.img_off = c.take<uint64_t>(ni + 8);
-    L.sp = np <= (size_t)SP_MAX_PLANES && g.npix >= SP_MIN_COUNT;
     if (L.sp) {
         const SpSizes z = sp_sizes((uint32_t)np, g.cap);
         L.spsz = z;
@@ -1060,7 +1098,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_PREFIX);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.grp_tot, 0, ((size_t)ngroups * 8 + 8) * sizeof(uint32_t), st));
-                k_prefix<<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
+                if (L.sp) k_prefix<true><<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
+                else k_prefix<false><<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
                 s.launched();
             }
             {
@@ -1092,20 +1131,25 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 StageScope s(ctx, ST_WALK, wst);
                 WalkArgs wa;
                 wa.resolved = L.sp_resolved;
-                wa.fine = L.fine; wa.blk_rec4 = (const uint4 *)L.blk_rec;
+                wa.fine = L.fine; wa.e_grp = L.e_grp; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
                 wa.cap = g.cap; wa.epcap = g.epcap;
                 // beside the speculative kernels every walker warp gets a whole SM (its shared-memory request leaves no room
                 // for other blocks): the walk is a latency chain, co-resident blocks would steal its issue slots
-                const size_t walk_smem = overlap ? (size_t)200 * 1024 : sizeof(WalkSmem);
-                unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, overlap ? 148 : 148 * 3);
                 static bool walk_attr_done = false;
                 if (!walk_attr_done) {
-                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                     walk_attr_done = true;
                 }
-                k_walk<<<blocks, 32, walk_smem, wst>>>(wa);
+                if (L.sp) {
+                    const size_t walk_smem = overlap ? (size_t)200 * 1024 : sizeof(WalkSmem<true>);
+                    unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, overlap ? 148 : 148 * 3);
+                    k_walk<true><<<blocks, 32, walk_smem, wst>>>(wa);
+                } else {
+                    unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 12);
+                    k_walk<false><<<blocks, 32, sizeof(WalkSmem<false>), wst>>>(wa);
+                }
                 s.launched();
                 return FELICS_OK;
             };
@@ -1149,8 +1193,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_KFILL);
                 size_t total = np * (size_t)g.cap;
-                k_kfill<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(L.fine, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec,
-                                                                         L.plane_used, g.cap, (uint32_t)np, L.k_grp);
+                const unsigned kblocks = (unsigned)((total + 255) / 256);
+                if (L.sp) k_kfill<true><<<kblocks, 256, 0, st>>>(L.fine, L.e_grp, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec, L.plane_used, g.cap, (uint32_t)np, L.k_grp);
+                else k_kfill<false><<<kblocks, 256, 0, st>>>(L.fine, L.e_grp, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec, L.plane_used, g.cap, (uint32_t)np, L.k_grp);
                 s.launched();
             }
             {
