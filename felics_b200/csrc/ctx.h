@@ -52,6 +52,10 @@ struct felics_ctx {
     void *pinned = nullptr;       // small pinned host buffer for read-backs
     size_t pinned_cap = 0;
 
+    // per-context (hence per-device) one-time kernel attribute settings
+    bool walk_attr_done = false, sp_attr_done = false;
+    size_t decode_smem_set = 0;
+
     bool prof = false;
     bool no_spec = false;         // debug/bench switch: skip the speculative walk
     std::vector<felics::ProfEntry> prof_pending;

@@ -643,10 +643,9 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
         StageScope s(ctx, ST_DECODE);
         const size_t smem = (size_t)(NBIN - 1) * NK * 4 + 8 + 2 * (size_t)hdr.width * sizeof(int16_t);
         if (hdr.width <= DEC_MAX_W && npix >= 1) {
-            static size_t attr_set = 0;
-            if (smem > 48 * 1024 && smem > attr_set) {
+            if (smem > 48 * 1024 && smem > ctx->decode_smem_set) {
                 FELICS_CUDA_TRY(cudaFuncSetAttribute(k_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_set = smem;
+                ctx->decode_smem_set = smem;
             }
             k_decode<<<(unsigned)n, 32, smem, st>>>(a, (uint32_t)n);
         } else {

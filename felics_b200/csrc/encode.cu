@@ -257,29 +257,46 @@ __device__ __forceinline__ void warp_scan3(uint32_t &u01, uint32_t &u23, uint32_
 
 // FINE = true: the per-element records are written (big single images: the speculative walk and the latency-bound
 // serial walk read them); FINE = false: only block records, the consumers redo the 32-element scan themselves.
+constexpr int PREFIX_THREADS = GROUP / 8;   // one thread per 8 consecutive elements, four threads per 32-block
 template <bool FINE>
-__global__ void __launch_bounds__(GROUP) k_prefix(const uint16_t *__restrict__ e_grp, uint32_t cap, uint32_t gpp,
-                                                  const uint32_t *__restrict__ plane_used, uint4 *__restrict__ fine,
-                                                  uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ grp_tot) {
+__global__ void __launch_bounds__(PREFIX_THREADS) k_prefix(const uint16_t *__restrict__ e_grp, uint32_t cap, uint32_t gpp,
+                                                           const uint32_t *__restrict__ plane_used, uint4 *__restrict__ fine,
+                                                           uint32_t *__restrict__ blk_rec, uint32_t *__restrict__ grp_tot) {
     __shared__ uint32_t tot[32][NK];
     uint32_t grp = blockIdx.x;
     uint32_t p = grp / gpp;
     uint32_t off = (grp - p * gpp) * GROUP;  // plane-relative element offset of this group
     if (off >= plane_used[p]) return;        // grp_tot stays 0 (memset)
-    size_t g = (size_t)p * cap + off + threadIdx.x;
-    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t e = e_grp[g];
-    uint32_t u01, u23, u45;
-    pack_costs(e, u01, u23, u45);
-    warp_scan3(u01, u23, u45, lane);
-    if (FINE) fine[g] = make_uint4(u01, u23, u45, e);
-    if (lane == 31) {
-        tot[wid][0] = u01 & 0xffffu; tot[wid][1] = u01 >> 16;
-        tot[wid][2] = u23 & 0xffffu; tot[wid][3] = u23 >> 16;
-        tot[wid][4] = u45 & 0xffffu; tot[wid][5] = u45 >> 16;
+    const size_t g = (size_t)p * cap + off + threadIdx.x * 8u;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint4 ev = *reinterpret_cast<const uint4 *>(e_grp + g);   // eight residuals
+    const uint32_t e[8] = {ev.x & 0xffffu, ev.x >> 16, ev.y & 0xffffu, ev.y >> 16, ev.z & 0xffffu, ev.z >> 16, ev.w & 0xffffu, ev.w >> 16};
+    uint32_t u01[8], u23[8], u45[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        pack_costs(e[i], u01[i], u23[i], u45[i]);
+        if (i) { u01[i] += u01[i - 1]; u23[i] += u23[i - 1]; u45[i] += u45[i - 1]; }   // inclusive inside my eight
+    }
+    // exclusive prefix over the four threads of my 32-block
+    uint32_t x01 = u01[7], x23 = u23[7], x45 = u45[7];
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, x01, o, 4), b = __shfl_up_sync(0xffffffffu, x23, o, 4), c = __shfl_up_sync(0xffffffffu, x45, o, 4);
+        if ((lane & 3u) >= (uint32_t)o) { x01 += a; x23 += b; x45 += c; }
+    }
+    const uint32_t b01 = x01 - u01[7], b23 = x23 - u23[7], b45 = x45 - u45[7];
+    if (FINE) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) fine[g + i] = make_uint4(u01[i] + b01, u23[i] + b23, u45[i] + b45, e[i]);
+    }
+    if ((lane & 3u) == 3u) {                 // the last quarter holds the block's totals
+        const uint32_t bi = threadIdx.x >> 2;
+        tot[bi][0] = x01 & 0xffffu; tot[bi][1] = x01 >> 16;
+        tot[bi][2] = x23 & 0xffffu; tot[bi][3] = x23 >> 16;
+        tot[bi][4] = x45 & 0xffffu; tot[bi][5] = x45 >> 16;
     }
     __syncthreads();
-    if (wid == 0) {
+    if (threadIdx.x < 32) {
         size_t blk = (size_t)grp * 32 + lane;
 #pragma unroll
         for (int k = 0; k < NK; k++) {
@@ -607,49 +624,61 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
     }
 }
 
-// kfill: one thread per grouped element.
-template <bool FINE>
-__global__ void __launch_bounds__(256) k_kfill(const uint4 *__restrict__ fine, const uint16_t *__restrict__ e_grp, const uint4 *__restrict__ blk_rec4,
+// kfill: k = argmin (ties to the largest k, parameter_selection.rs:78-83) of the counters before every out-of-range
+// element.  One thread per eight consecutive elements (four threads per 32-block): the costs are re-derived from the
+// residuals and scanned over the block, the epoch bases come from the walk's records.
+__global__ void __launch_bounds__(256) k_kfill(const uint16_t *__restrict__ e_grp, const uint4 *__restrict__ blk_rec4,
                                                const uint32_t *__restrict__ blk_epoch, const uint4 *__restrict__ ep_rec,
                                                const uint32_t *__restrict__ plane_used, uint32_t cap, uint32_t np,
                                                uint8_t *__restrict__ k_grp) {
-    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t p = (uint32_t)(g / cap);
+    const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8u;
+    const uint32_t p = (uint32_t)(g / cap);
     if (p >= np) return;
-    uint32_t off = (uint32_t)(g - (size_t)p * cap);
-    if (off >= plane_used[p]) return;   // whole warps: plane_used and cap are multiples of 32
-    uint4 f;
-    if (FINE) {
-        f = fine[g];
-    } else {
-        f.w = e_grp[g];
-        pack_costs(f.w, f.x, f.y, f.z);
-        warp_scan3(f.x, f.y, f.z, threadIdx.x & 31u);
-    }
-    if (f.w == PAD_E) return;
-    size_t blk = g >> 5;
-    uint32_t ep = blk_epoch[blk];
-    uint4 b1 = ep_rec[(size_t)ep * 2 + 1];
-    for (;;) {
-        uint4 n1 = ep_rec[(size_t)ep * 2 + 3];
-        if (n1.z > (uint32_t)g) break;
-        ep++;
-        b1 = n1;
-    }
-    const uint4 b0 = ep_rec[(size_t)ep * 2];
-    uint32_t e = f.w;
-    uint32_t U[NK];
-    unpack6(f, U);
-    const uint4 e0 = blk_rec4[blk * 4], e1 = blk_rec4[blk * 4 + 1];
-    const uint32_t cps[NK] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y};
-    const uint32_t eb[NK] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y};
-    uint32_t v[NK];
+    const uint32_t off = (uint32_t)(g - (size_t)p * cap);
+    if (off >= plane_used[p]) return;   // whole warps: plane_used and cap are multiples of 256
+    const uint32_t lane = threadIdx.x & 31;
+    const uint4 ev = *reinterpret_cast<const uint4 *>(e_grp + g);
+    const uint32_t e[8] = {ev.x & 0xffffu, ev.x >> 16, ev.y & 0xffffu, ev.y >> 16, ev.z & 0xffffu, ev.z >> 16, ev.w & 0xffffu, ev.w >> 16};
+    uint32_t x01[8], x23[8], x45[8];    // cost of the elements before element i inside my eight
+    uint32_t t01 = 0, t23 = 0, t45 = 0;
 #pragma unroll
-    for (int k = 0; k < NK; k++) {
-        uint32_t d = (e >> k) + 1u + (uint32_t)k;
-        v[k] = eb[k] + cps[k] + U[k] - d;   // counters before this element's update
+    for (int i = 0; i < 8; i++) {
+        uint32_t a, b, c;
+        pack_costs(e[i], a, b, c);
+        x01[i] = t01; x23[i] = t23; x45[i] = t45;
+        t01 += a; t23 += b; t45 += c;
     }
-    k_grp[g] = (uint8_t)argmin_last(v);
+    uint32_t s01 = t01, s23 = t23, s45 = t45;
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, s01, o, 4), b = __shfl_up_sync(0xffffffffu, s23, o, 4), c = __shfl_up_sync(0xffffffffu, s45, o, 4);
+        if ((lane & 3u) >= (uint32_t)o) { s01 += a; s23 += b; s45 += c; }
+    }
+    s01 -= t01; s23 -= t23; s45 -= t45;   // cost of the block's elements before my eight
+    const size_t blk = g >> 5;
+    const uint4 c0 = blk_rec4[blk * 4], c1 = blk_rec4[blk * 4 + 1];
+    // counters before element i = epoch base + prefix at the block start + costs inside the block before i
+    const uint32_t q[NK] = {c0.x + (s01 & 0xffffu), c0.y + (s01 >> 16), c0.z + (s23 & 0xffffu), c0.w + (s23 >> 16), c1.x + (s45 & 0xffffu), c1.y + (s45 >> 16)};
+    uint32_t ep = blk_epoch[blk];
+    uint4 b0 = ep_rec[(size_t)ep * 2], b1 = ep_rec[(size_t)ep * 2 + 1];
+    uint32_t next = ep_rec[(size_t)ep * 2 + 3].z;   // first element of the following epoch (0xFFFFFFFF after the last one)
+    uint32_t kk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t gi = (uint32_t)g + i;
+        while (next <= gi) {
+            ep++;
+            b0 = ep_rec[(size_t)ep * 2]; b1 = ep_rec[(size_t)ep * 2 + 1];
+            next = ep_rec[(size_t)ep * 2 + 3].z;
+        }
+        const uint32_t v[NK] = {b0.x + q[0] + (x01[i] & 0xffffu), b0.y + q[1] + (x01[i] >> 16), b0.z + q[2] + (x23[i] & 0xffffu),
+                                b0.w + q[3] + (x23[i] >> 16), b1.x + q[4] + (x45[i] & 0xffffu), b1.y + q[5] + (x45[i] >> 16)};
+        kk[i] = (uint32_t)argmin_last(v);
+    }
+    uint2 out;
+    out.x = kk[0] | (kk[1] << 8) | (kk[2] << 16) | (kk[3] << 24);
+    out.y = kk[4] | (kk[5] << 8) | (kk[6] << 16) | (kk[7] << 24);
+    *reinterpret_cast<uint2 *>(k_grp + g) = out;
 }
 
 // ------------------------------------------------------------------------------------
@@ -1098,8 +1127,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_PREFIX);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.grp_tot, 0, ((size_t)ngroups * 8 + 8) * sizeof(uint32_t), st));
-                if (L.sp) k_prefix<true><<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
-                else k_prefix<false><<<ngroups, GROUP, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
+                if (L.sp) k_prefix<true><<<ngroups, PREFIX_THREADS, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
+                else k_prefix<false><<<ngroups, PREFIX_THREADS, 0, st>>>(L.e_grp, g.cap, g.gpp, L.plane_used, L.fine, L.blk_rec, L.grp_tot);
                 s.launched();
             }
             {
@@ -1137,10 +1166,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 wa.cap = g.cap; wa.epcap = g.epcap;
                 // beside the speculative kernels every walker warp gets a whole SM (its shared-memory request leaves no room
                 // for other blocks): the walk is a latency chain, co-resident blocks would steal its issue slots
-                static bool walk_attr_done = false;
-                if (!walk_attr_done) {
+                if (!ctx->walk_attr_done) {
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                    walk_attr_done = true;
+                    ctx->walk_attr_done = true;
                 }
                 if (L.sp) {
                     const size_t walk_smem = overlap ? (size_t)200 * 1024 : sizeof(WalkSmem<true>);
@@ -1167,10 +1195,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.trow = L.sp_trow;
                 sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch; sa.resolved = L.sp_resolved; sa.dbg = L.counters;
                 sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz;
-                static bool attr_done = false;
-                if (!attr_done) {
+                if (!ctx->sp_attr_done) {
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
-                    attr_done = true;
+                    ctx->sp_attr_done = true;
                 }
                 const SpSizes &z = L.spsz;
                 k_sp_plan<<<1, NBIN, 0, st>>>(sa);
@@ -1193,9 +1220,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_KFILL);
                 size_t total = np * (size_t)g.cap;
-                const unsigned kblocks = (unsigned)((total + 255) / 256);
-                if (L.sp) k_kfill<true><<<kblocks, 256, 0, st>>>(L.fine, L.e_grp, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec, L.plane_used, g.cap, (uint32_t)np, L.k_grp);
-                else k_kfill<false><<<kblocks, 256, 0, st>>>(L.fine, L.e_grp, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec, L.plane_used, g.cap, (uint32_t)np, L.k_grp);
+                const unsigned kblocks = (unsigned)((total / 8 + 255) / 256);
+                k_kfill<<<kblocks, 256, 0, st>>>(L.e_grp, (const uint4 *)L.blk_rec, L.blk_epoch, (const uint4 *)L.ep_rec, L.plane_used, g.cap, (uint32_t)np, L.k_grp);
                 s.launched();
             }
             {
