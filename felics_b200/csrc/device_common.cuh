@@ -26,39 +26,48 @@ struct PixelClass {
     int lo;
 };
 
+// Raster cursor over one plane: position (i, x, y) and a pointer to the sample, advanced by a fixed step.
 // T = uint8_t (gray samples straight from the caller's pixels) or int16_t (Y/Co/Cg planes).
 template <typename T>
-__device__ __forceinline__ PixelClass classify_pixel_xy(const T *__restrict__ pl, uint32_t i, uint32_t x, uint32_t y, uint32_t w) {
-    uint32_t a, b;
-    if (x > 0 && y > 0) { a = i - 1; b = i - w; }            // left, up
-    else if (y == 0) { a = i - 1; b = i - 2; }               // first row (x >= 2 because i >= 2)
-    else if (y >= 2) { a = i - w; b = i - 2 * w; }           // first column
-    else { a = i - w; b = i - w + 1; }                       // (0,1): up, up-right
-    int p = pl[i], v1 = pl[a], v2 = pl[b];
-    int h = max(v1, v2), l = min(v1, v2);
-    PixelClass r;
-    r.delta = h - l;
-    r.lo = l;
-    if (p < l) { r.cls = 2; r.val = l - p - 1; }
-    else if (p > h) { r.cls = 1; r.val = p - h - 1; }
-    else { r.cls = 0; r.val = p - l; }
-    return r;
-}
-template <typename T>
-__device__ __forceinline__ PixelClass classify_pixel(const T *__restrict__ pl, uint32_t i, uint32_t w) {
-    uint32_t y = i / w;
-    return classify_pixel_xy(pl, i, i - y * w, y, w);
-}
-// raster position (x, y) of pixel i after moving `step` pixels forward; one division only for narrow images
-__device__ __forceinline__ void advance_xy(uint32_t &x, uint32_t &y, uint32_t i_new, uint32_t step, uint32_t w) {
-    if (w >= step) {
-        x += step;
-        if (x >= w) { x -= w; y++; }
-    } else {
-        y = i_new / w;
-        x = i_new - y * w;
+struct RasterCursor {
+    const T *pp;       // &plane[i]
+    uint32_t i, x, y, w;
+    __device__ __forceinline__ void init(const T *plane, uint32_t i0, uint32_t width) {
+        w = width; i = i0; y = i0 / width; x = i0 - y * width; pp = plane + i0;
     }
-}
+    __device__ __forceinline__ void step(uint32_t s) {
+        i += s; pp += s;
+        if (w >= s) {                      // at most one row boundary per step
+            x += s;
+            if (x >= w) { x -= w; y++; }
+        } else {                           // narrow images: one division
+            y = i / w; x = i - y * w;
+        }
+    }
+    // neighbours and class of the sample under the cursor (misc.rs:6-24, compression.rs:118-145); needs i >= 2
+    __device__ __forceinline__ PixelClass classify() const {
+        const int p = pp[0];
+        int v1, v2;
+        if (x > 0 && y > 0) {              // interior: left, up
+            v1 = pp[-1];
+            v2 = *(pp - w);
+        } else if (y == 0) {               // first row (x >= 2 because i >= 2): i-1, i-2
+            v1 = pp[-1]; v2 = pp[-2];
+        } else if (y >= 2) {               // first column: up, up-up
+            v1 = *(pp - w); v2 = *(pp - 2 * (size_t)w);
+        } else {                           // pixel (0,1): up, up-right
+            v1 = *(pp - w); v2 = *(pp - w + 1);
+        }
+        const int h = max(v1, v2), l = min(v1, v2);
+        PixelClass r;
+        r.delta = h - l;
+        r.lo = l;
+        const bool below = p < l, above = p > h;
+        r.cls = below ? 2 : (above ? 1 : 0);
+        r.val = below ? l - p - 1 : (above ? p - h - 1 : p - l);
+        return r;
+    }
+};
 
 // Phased-in code of v in [0, n-1] (phase_in_coding.rs:23-84): returns the code value, sets len.
 // long codeword = (x - right_p)/2 + right_p in m bits followed by (x - right_p)&1  ==  x + right_p in m+1 bits.

@@ -62,16 +62,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist(const T *__restrict__ pla
     __syncthreads();
     const T *pl = planes + (size_t)p * npix;
     uint32_t start = t * TILE;
-    uint32_t i = start + threadIdx.x;
-    uint32_t y = i / w, x = i - y * w;
+    RasterCursor<T> cur;
+    cur.init(pl, start + threadIdx.x, w);
 #pragma unroll 4
     for (int j = 0; j < TILE / TILE_THREADS; j++) {
-        if (i >= 2 && i < npix) {
-            PixelClass pc = classify_pixel_xy(pl, i, x, y, w);
+        if (cur.i >= 2 && cur.i < npix) {
+            PixelClass pc = cur.classify();
             if (pc.cls != 0) atomicAdd(&h[pc.delta], 1u);
         }
-        i += TILE_THREADS;
-        advance_xy(x, y, i, TILE_THREADS, w);
+        cur.step(TILE_THREADS);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) {
@@ -158,7 +157,7 @@ __global__ void __launch_bounds__(NBIN) k_tilebase(uint32_t *__restrict__ tile_h
 // and visits them 32 consecutive pixels at a time, so ranks follow raster order.
 // ------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(TILE_THREADS) k_scatter(const T *__restrict__ planes, uint32_t w, uint32_t npix,
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_scatter(const T *__restrict__ planes, uint32_t w, uint32_t npix,
                                                           uint32_t tpp, uint32_t cap, const uint32_t *__restrict__ tile_base,
                                                           uint16_t *__restrict__ e_grp, uint32_t *__restrict__ gidx) {
     __shared__ uint16_t wcnt[TILE_WARPS][NBIN];
@@ -173,14 +172,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const T *__restrict__ 
     uint32_t info[WARP_ITERS];  // rank(13) | delta(9) << 13 | oor << 22
     uint16_t ev[WARP_ITERS];
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t py = (wstart + lane) / w, px = wstart + lane - py * w;
+    RasterCursor<T> cur;
+    cur.init(pl, wstart + lane, w);
 #pragma unroll
     for (int it = 0; it < WARP_ITERS; it++) {
-        uint32_t i = wstart + it * 32 + lane;
+        const uint32_t i = cur.i;
         bool oor = false;
         int delta = 0, val = 0;
         if (i >= 2 && i < npix) {
-            PixelClass pc = classify_pixel_xy(pl, i, px, py, w);
+            PixelClass pc = cur.classify();
             oor = pc.cls != 0;
             delta = pc.delta;
             val = pc.val;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_scatter(const T *__restrict__ 
         __syncwarp();
         info[it] = rank | ((uint32_t)delta << 13) | (oor ? (1u << 22) : 0u);
         ev[it] = (uint16_t)val;
-        advance_xy(px, py, i + 32, 32, w);
+        cur.step(32);
     }
     __syncthreads();
     // exclusive prefix over warps, per context, on top of the tile's base
@@ -695,14 +695,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code(const T *__restrict__ pla
     const T *pl = planes + (size_t)p * npix;
     uint32_t start = t * TILE;
     uint32_t bits = 0;
-    uint32_t i = start + threadIdx.x;
-    uint32_t y = i / w, x = i - y * w;
+    RasterCursor<T> cur;
+    cur.init(pl, start + threadIdx.x, w);
 #pragma unroll 4
-    for (int j = 0; j < TILE / TILE_THREADS; j++, i += TILE_THREADS) {
+    for (int j = 0; j < TILE / TILE_THREADS; j++) {
+        const uint32_t i = cur.i;
         if (i >= npix) break;
         uint32_t r = 0;
         if (i >= 2) {
-            PixelClass pc = classify_pixel_xy(pl, i, x, y, w);
+            PixelClass pc = cur.classify();
             if (pc.cls == 0) {
                 int len;
                 uint32_t code = phase_in_code((uint32_t)pc.delta + 1u, (uint32_t)pc.val, len);
@@ -726,7 +727,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code(const T *__restrict__ pla
         }
         rec[(size_t)p * npix + i] = r;
         bits += rec_len(r);
-        advance_xy(x, y, i + TILE_THREADS, TILE_THREADS, w);
+        cur.step(TILE_THREADS);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
