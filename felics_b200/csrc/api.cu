@@ -116,6 +116,8 @@ int felics_ctx_create(int device, felics_ctx **out) {
     {
         const char *ns = getenv("FELICS_B200_NO_SPEC");   // debug switch: force the serial epoch walk
         ctx->no_spec = ns && ns[0] == '1';
+        const char *no = getenv("FELICS_B200_NO_OVERLAP");   // profiling switch: one stream, kernels back to back
+        ctx->no_overlap = no && no[0] == '1';
     }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return FELICS_ERR_CUDA; }

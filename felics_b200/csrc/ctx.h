@@ -57,6 +57,7 @@ struct felics_ctx {
     size_t decode_smem_set = 0;
 
     bool prof = false;
+    bool no_overlap = false;      // debug/profiling switch: run the serial walk after the speculative one, on the same stream
     bool no_spec = false;         // debug/bench switch: skip the speculative walk
     std::vector<felics::ProfEntry> prof_pending;
     std::vector<cudaEvent_t> event_pool;

@@ -1145,7 +1145,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             // With the speculative walk on, the serial walker starts at the same time on a second stream: it walks
             // every chain and drops a chain as soon as the speculation has resolved it (both write identical
             // records), so the speculation's latency is hidden behind the chains that must be walked serially.
-            const bool overlap = L.sp && !ctx->no_spec;
+            const bool overlap = L.sp && !ctx->no_spec && !ctx->no_overlap;
             cudaStream_t wst = st;
             if (overlap) {
                 if (!ctx->side) {

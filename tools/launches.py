@@ -4,9 +4,11 @@ path = sys.argv[1]
 with open(path) as f:
     lines = [l for l in f if not l.startswith('==')]
 rows = [r for r in csv.DictReader(lines) if r['Metric Name'] == 'gpu__time_duration.sum']
-names = [(r['Kernel Name'].split('(')[0], float(r['Metric Value'].replace(',', ''))) for r in rows]
-# the last encode starts at the last k_to_planes launch
-start = max(i for i, (n, _) in enumerate(names) if n.startswith('k_to_planes'))
+names = [(r['Kernel Name'].split('(')[0].replace('void ', ''), float(r['Metric Value'].replace(',', ''))) for r in rows]
+# the last encode starts at the last histogram launch (preceded by the plane conversion for RGB)
+start = max(i for i, (n, _) in enumerate(names) if 'k_hist' in n)
+if start and 'k_to_planes' in names[start - 1][0]:
+    start -= 1
 tot = 0
 for n, v in names[start:]:
     print(f"{n:28s} {v / 1000:9.1f} us")
