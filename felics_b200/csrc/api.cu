@@ -118,6 +118,8 @@ int felics_ctx_create(int device, felics_ctx **out) {
         ctx->no_spec = ns && ns[0] == '1';
         const char *no = getenv("FELICS_B200_NO_OVERLAP");   // profiling switch: one stream, kernels back to back
         ctx->no_overlap = no && no[0] == '1';
+        const char *nh = getenv("FELICS_B200_NO_HOP");       // debug switch: no segment hops
+        ctx->no_hop = nh && nh[0] == '1';
     }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return FELICS_ERR_CUDA; }

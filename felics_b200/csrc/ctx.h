@@ -53,11 +53,12 @@ struct felics_ctx {
     size_t pinned_cap = 0;
 
     // per-context (hence per-device) one-time kernel attribute settings
-    bool walk_attr_done = false, sp_attr_done = false;
+    bool walk_attr_done = false, sp_attr_done = false, hop_attr_done = false;
     size_t decode_smem_set = 0;
 
     bool prof = false;
     bool no_overlap = false;      // debug/profiling switch: run the serial walk after the speculative one, on the same stream
+    bool no_hop = false;          // debug switch: no segment hops in the serial walker
     bool no_spec = false;         // debug/bench switch: skip the speculative walk
     std::vector<felics::ProfEntry> prof_pending;
     std::vector<cudaEvent_t> event_pool;

@@ -23,6 +23,7 @@
 #include <cstring>
 
 #include "sp_walk.cuh"
+#include "hop_walk.cuh"
 
 namespace felics {
 
@@ -429,6 +430,9 @@ struct WalkArgs {
     uint32_t cap;           // grouped elements per plane
     uint32_t epcap;         // epoch records per plane
     const uint8_t *resolved; // per (plane, context): 1 = already resolved by the speculative walk (may be null)
+    HopTables hop;           // segment hops for rejected chains (hop.ready == nullptr: off)
+    const SpDesc *desc;
+    const uint32_t *chain_fail;
 };
 
 __device__ __forceinline__ void unpack6(const uint4 &f, uint32_t U[NK]) {
@@ -542,27 +546,105 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 bulk_g2s(&sblk[buf][0], a.blk_rec4 + (blk0 + w * 32u) * 4, nb * 64u, &bars[buf]);
             }
         };
-        uint32_t issued = min(nwin, (uint32_t)WALK_BUF - 1u);   // windows whose copy has been started
-        for (uint32_t w = 0; w < issued; w++) prefetch(w);
         bool aborted = false;   // the speculative walk (running beside this kernel) resolved the chain
-        uint32_t flag = 0;      // resolved[pc], polled one window ahead so that the load never stalls the walk
-
+        uint32_t flag = 0;      // resolved[pc], polled ahead of its use so that the load never stalls the walk
         uint32_t nep = 1;       // epochs recorded so far
         uint32_t cur = 0;       // chain-relative first element of the current epoch
         bool overflow = false;
-        for (uint32_t w = 0; w < issued; w++) {
-            const uint32_t buf = w % WALK_BUF;
+        // segment hops (hop_walk.cuh): once the tables of a chain the speculation rejected are ready, a segment whose
+        // entry state passes the threshold tests is crossed with one lookup instead of being walked
+        bool hop_on = false;
+        uint32_t hop_seg0 = 0, hop_kb = 0, hop_skip = 0, hop_fails = 0, ready = 0;
+        bool abs_state = false; // after a hop the counters are held as plain values at the start of window w
+        uint32_t S[NK] = {0, 0, 0, 0, 0, 0};
+        uint32_t w = 0;         // next window to process
+        uint32_t issued = 0;    // next window to copy; windows [w, issued) are in flight
+        uint32_t polls = 0;
+        while (w < nwin) {
             if (flag == 1) aborted = true;
-            if (a.resolved && (w & 31u) == 0) flag = *reinterpret_cast<const volatile uint8_t *>(a.resolved + pc);
-            if (!aborted && issued < nwin) { prefetch(issued); issued++; }   // its buffer was consumed in the previous iteration
+            if ((polls++ & 31u) == 0) {
+                if (a.resolved) flag = *reinterpret_cast<const volatile uint8_t *>(a.resolved + pc);
+                if (FINE && a.hop.ready && !hop_on && ready == 0) ready = *reinterpret_cast<const volatile uint32_t *>(a.hop.ready);
+            }
+            if (FINE && ready == 1 && !hop_on) {
+                ready = 2;
+                const uint32_t di = a.hop.pc2desc[pc];
+                if (di != 0xFFFFFFFFu && *reinterpret_cast<const volatile uint32_t *>(a.chain_fail + di) == SP_OK - 1) {
+                    hop_on = true;
+                    hop_seg0 = a.desc[di].seg0;
+                    hop_kb = a.desc[di].kb;
+                    hop_skip = (w >> 2) + 1;   // first attempt at the next segment boundary
+                }
+            }
+            if (aborted) {
+                // only drain the copies in flight
+                if (w < issued) { const uint32_t buf = w % WALK_BUF; mbar_wait(&bars[buf], (phases >> buf) & 1u); phases ^= 1u << buf; w++; continue; }
+                break;
+            }
+            const uint32_t seg = w >> 2;
+            if (FINE && hop_on && (w & 3u) == 0 && seg >= hop_skip && issued == w) {
+                // ---- try to hop over segment `seg` (windows w .. w+3) ----
+                const uint4 t0 = a.blk_rec4[(blk0 + (size_t)w * 32u) * 4], t1 = a.blk_rec4[(blk0 + (size_t)w * 32u) * 4 + 1];
+                if (!abs_state) {
+                    S[0] = base[0] + t0.x; S[1] = base[1] + t0.y; S[2] = base[2] + t0.z; S[3] = base[3] + t0.w; S[4] = base[4] + t1.x; S[5] = base[5] + t1.y;
+                }
+                uint32_t x = S[0], mine = S[0];
+#pragma unroll
+                for (uint32_t k = 1; k < NK; k++) { x = hop_kb == k ? S[k] : x; mine = lane == k ? S[k] : mine; }
+                const size_t slot = hop_seg0 + seg;
+                bool good = x >= 1u && x <= HALVE_AT;
+                uint32_t xn = 0, th = 0, dt = 0;
+                unsigned long long A = 0;
+                if (good) {
+                    xn = a.hop.xn[slot * 1024 + (x - 1u)];
+                    if (lane < NK) {
+                        const size_t t = (slot * NK + lane) * 1024 + (x - 1u);
+                        th = a.hop.theta[t]; A = a.hop.A[t]; dt = a.hop.dt[t];
+                    }
+                }
+                const uint32_t n = xn >> 16;
+                good = good && n != HOP_INVALID && nep + n + 1 < ep_room;
+                good = __all_sync(0xffffffffu, good && (lane >= NK || lane == hop_kb || mine >= th));
+                if (good) {
+                    if (lane < 8) a.hop.log[slot * 8 + lane] = lane < NK ? mine : (lane == 6 ? nep : 1u);
+                    const uint32_t mynew = lane == hop_kb ? (xn & 0xffffu) : (uint32_t)(((unsigned long long)mine + A) >> n) + dt;
+#pragma unroll
+                    for (uint32_t k = 0; k < NK; k++) S[k] = __shfl_sync(0xffffffffu, mynew, k);
+                    nep += n;
+                    abs_state = true;
+                    w = min(w + 4u, nwin);
+                    issued = w;
+                    hop_fails = 0;
+                    continue;
+                }
+                hop_fails++;
+                hop_skip = seg + 1 + (hop_fails >= 2 ? min(1u << (hop_fails - 2), 64u) : 0u);
+            }
+            // ---- stream mode: walk window w element-exactly ----
+            {
+                // copies run ahead, but not across a segment boundary where a hop will be tried
+                uint32_t limit = nwin;
+                if (FINE && hop_on) {
+                    const uint32_t nb = max(seg + 1, hop_skip);      // next segment that will be tried
+                    limit = min(nwin, nb * 4u);
+                }
+                while (issued < limit && issued < w + (uint32_t)WALK_BUF) { prefetch(issued); issued++; }   // window w+3 reuses the buffer of w-1
+            }
+            const uint32_t buf = w % WALK_BUF;
             mbar_wait(&bars[buf], (phases >> buf) & 1u);
             phases ^= 1u << buf;
-            if (aborted) continue;                                          // only drain the copies in flight
             const uint4 *wf = &sfine[FINE ? buf : 0][0];
             const uint16_t *we = &se[FINE ? 0 : buf][0];
             const uint4 *wb = &sblk[buf][0];
             const uint32_t wblk0 = w * 32u;
             const bool valid = wblk0 + lane < nblk;
+            if (abs_state) {
+                // back from plain values to re-based ones: base = S - T(window start); the open epoch began before this window
+                const uint4 t0 = wb[0], t1 = wb[1];
+                base[0] = S[0] - t0.x; base[1] = S[1] - t0.y; base[2] = S[2] - t0.z; base[3] = S[3] - t0.w; base[4] = S[4] - t1.x; base[5] = S[5] - t1.y;
+                cur = wblk0 * 32u;
+                abs_state = false;
+            }
             uint32_t incl[NK];
             {
                 const uint4 r2 = wb[lane * 4 + 2], r3 = wb[lane * 4 + 3];
@@ -616,6 +698,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             }
             if (valid) a.blk_epoch[blk0 + wblk0 + lane] = ep0 + my_epoch;
             __syncwarp();
+            w++;
         }
         if (lane == 0 && !aborted) {
             if (overflow) atomicOr(&a.counters[2], 1u);
@@ -982,6 +1065,8 @@ struct Layout {
     uint4 *sp_trow;
     unsigned long long *sp_ablk;
     uint8_t *sp_resolved;
+    HopTables hop;
+    uint32_t *sp_pc2desc;
     size_t bytes;
 };
 
@@ -1032,6 +1117,14 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
         L.sp_chain_n = c.take<uint32_t>(z.max_desc);
         L.sp_chain_fail = c.take<uint32_t>(z.max_desc);
         L.sp_trow = c.take<uint4>(((size_t)np * g.epcap + 8) * 2);
+        L.sp_pc2desc = c.take<uint32_t>(np * NBIN);
+        L.hop.xn = c.take<uint32_t>((size_t)z.max_seg * 1024);
+        L.hop.theta = c.take<uint32_t>((size_t)z.max_seg * NK * 1024);
+        L.hop.A = c.take<unsigned long long>((size_t)z.max_seg * NK * 1024);
+        L.hop.dt = c.take<uint32_t>((size_t)z.max_seg * NK * 1024);
+        L.hop.log = c.take<uint32_t>((size_t)z.max_seg * 8 + 8);   // + the ready flag
+        L.hop.ready = L.hop.log ? L.hop.log + (size_t)z.max_seg * 8 : nullptr;
+        L.hop.pc2desc = L.sp_pc2desc;
         L.sp_ablk = c.take<unsigned long long>((size_t)z.max_eb * 8);
     }
     L.sp_resolved = c.take<uint8_t>(np * NBIN);
@@ -1148,6 +1241,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             const bool overlap = L.sp && !ctx->no_spec && !ctx->no_overlap;
             cudaStream_t wst = st;
             if (overlap) {
+                FELICS_CUDA_TRY(cudaMemsetAsync(L.hop.log, 0, ((size_t)L.spsz.max_seg * 8 + 8) * sizeof(uint32_t), st));
+                FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_pc2desc, 0xFF, np * NBIN * sizeof(uint32_t), st));
                 if (!ctx->side) {
                     FELICS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
                     FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -1161,6 +1256,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 StageScope s(ctx, ST_WALK, wst);
                 WalkArgs wa;
                 wa.resolved = L.sp_resolved;
+                wa.hop = L.hop; wa.desc = L.sp_desc; wa.chain_fail = L.sp_chain_fail;
+                if (!overlap || ctx->no_hop) wa.hop.ready = nullptr;
                 wa.fine = L.fine; wa.e_grp = L.e_grp; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
@@ -1195,7 +1292,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 sa.map = L.sp_map; sa.pre = L.sp_pre; sa.gmap = L.sp_gmap; sa.grp_xin = L.sp_grp_xin; sa.grp_nbefore = L.sp_grp_nbefore;
                 sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.trow = L.sp_trow;
                 sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch; sa.resolved = L.sp_resolved; sa.dbg = L.counters;
-                sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz;
+                sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz; sa.pc2desc = overlap ? L.sp_pc2desc : nullptr;
                 if (!ctx->sp_attr_done) {
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
                     ctx->sp_attr_done = true;
@@ -1211,9 +1308,29 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_finish<true><<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
                 s.launched(9);
+                if (overlap && !ctx->no_hop) {
+                    // tables for segment hops over the chains that failed the verification; the walker (already running
+                    // on the other stream) starts using them when the ready flag appears
+                    if (!ctx->hop_attr_done) {
+                        FELICS_CUDA_TRY(cudaFuncSetAttribute(k_hop_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HopSmem)));
+                        ctx->hop_attr_done = true;
+                    }
+                    k_hop_maps<<<z.max_seg, 1024, sizeof(HopSmem), st>>>(sa, L.hop);
+                    k_hop_ready<<<1, 1, 0, st>>>(L.hop);
+                    s.launched(2);
+                }
             }
             if (overlap) {
                 FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+                if (!ctx->no_hop) {
+                    StageScope s(ctx, ST_SPEC);
+                    SpArgs sa;
+                    sa.fine = L.fine; sa.blk_rec4 = (const uint4 *)L.blk_rec; sa.desc = L.sp_desc; sa.seg_desc = L.sp_seg_desc; sa.counts = L.sp_counts;
+                    sa.trow = L.sp_trow; sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch;
+                    k_hop_emit<<<(L.spsz.max_seg + 3) / 4, 128, 0, st>>>(sa, L.hop);
+                    k_hop_finish<<<(L.spsz.max_seg + 3) / 4, 128, 0, st>>>(sa, L.hop);
+                    s.launched(2);
+                }
             } else {
                 int wrc = launch_walk();
                 if (wrc) return wrc;

@@ -66,6 +66,7 @@ struct SpArgs {
     uint32_t *blk_epoch;
     uint8_t *resolved;          // [plane*512 + context]: 1 when the chain needs no serial walk
     uint32_t *dbg;              // encode counters: [3] chains tried, [4] chains resolved
+    uint32_t *pc2desc;          // [plane*512 + context] -> descriptor index (may be null)
     uint32_t np, cap, epcap;
     SpSizes sz;
 };
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(NBIN) k_sp_plan(SpArgs a) {
             d.kb = kb;
             a.desc[di] = d;
             a.chain_fail[di] = SP_OK;
+            if (a.pc2desc) a.pc2desc[pc] = di;
         }
     }
     __syncthreads();
