@@ -328,7 +328,7 @@ class Codec:
 
     def debug_counters(self) -> np.ndarray:
         """Device counters of the last encode: [0] live chains, [2] error flags, [3] chains tried by the
-        speculative walk, [4] chains it resolved."""
+        speculative walk, [4] chains it resolved, [5] segments crossed by a hop, [6] hops refused."""
         out = np.zeros(8, dtype=np.uint32)
         self._lib.felics_debug_counters(self._h, out.ctypes.data)
         return out

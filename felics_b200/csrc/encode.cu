@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
         // segment hops (hop_walk.cuh): once the tables of a chain the speculation rejected are ready, a segment whose
         // entry state passes the threshold tests is crossed with one lookup instead of being walked
         bool hop_on = false;
-        uint32_t hop_seg0 = 0, hop_kb = 0, hop_skip = 0, hop_fails = 0, ready = 0;
+        uint32_t hop_seg0 = 0, hop_kb = 0, hop_skip = 0, hop_fails = 0, ready = 0, hops_done = 0, hops_refused = 0;
         bool abs_state = false; // after a hop the counters are held as plain values at the start of window w
         uint32_t S[NK] = {0, 0, 0, 0, 0, 0};
         uint32_t w = 0;         // next window to process
@@ -615,9 +615,11 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                     w = min(w + 4u, nwin);
                     issued = w;
                     hop_fails = 0;
+                    hops_done++;
                     continue;
                 }
                 hop_fails++;
+                hops_refused++;
                 hop_skip = seg + 1 + (hop_fails >= 2 ? min(1u << (hop_fails - 2), 64u) : 0u);
             }
             // ---- stream mode: walk window w element-exactly ----
@@ -700,6 +702,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             __syncwarp();
             w++;
         }
+        if (lane == 0 && (hops_done | hops_refused)) { atomicAdd(&a.counters[5], hops_done); atomicAdd(&a.counters[6], hops_refused); }
         if (lane == 0 && !aborted) {
             if (overflow) atomicOr(&a.counters[2], 1u);
             else rec[2 * nep + 1] = make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);  // sentinel
@@ -1240,9 +1243,12 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             // records), so the speculation's latency is hidden behind the chains that must be walked serially.
             const bool overlap = L.sp && !ctx->no_spec && !ctx->no_overlap;
             cudaStream_t wst = st;
-            if (overlap) {
+            const bool hops = L.sp && !ctx->no_spec && !ctx->no_hop;   // segment hops over rejected chains (hop_walk.cuh)
+            if (hops) {
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.hop.log, 0, ((size_t)L.spsz.max_seg * 8 + 8) * sizeof(uint32_t), st));
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.sp_pc2desc, 0xFF, np * NBIN * sizeof(uint32_t), st));
+            }
+            if (overlap) {
                 if (!ctx->side) {
                     FELICS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
                     FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
@@ -1257,7 +1263,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 WalkArgs wa;
                 wa.resolved = L.sp_resolved;
                 wa.hop = L.hop; wa.desc = L.sp_desc; wa.chain_fail = L.sp_chain_fail;
-                if (!overlap || ctx->no_hop) wa.hop.ready = nullptr;
+                if (!hops) wa.hop.ready = nullptr;
                 wa.fine = L.fine; wa.e_grp = L.e_grp; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
@@ -1292,7 +1298,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 sa.map = L.sp_map; sa.pre = L.sp_pre; sa.gmap = L.sp_gmap; sa.grp_xin = L.sp_grp_xin; sa.grp_nbefore = L.sp_grp_nbefore;
                 sa.chain_n = L.sp_chain_n; sa.chain_fail = L.sp_chain_fail; sa.ablk = L.sp_ablk; sa.trow = L.sp_trow;
                 sa.ep_rec = (uint4 *)L.ep_rec; sa.blk_epoch = L.blk_epoch; sa.resolved = L.sp_resolved; sa.dbg = L.counters;
-                sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz; sa.pc2desc = overlap ? L.sp_pc2desc : nullptr;
+                sa.np = (uint32_t)np; sa.cap = g.cap; sa.epcap = g.epcap; sa.sz = L.spsz; sa.pc2desc = hops ? L.sp_pc2desc : nullptr;
                 if (!ctx->sp_attr_done) {
                     FELICS_CUDA_TRY(cudaFuncSetAttribute(k_sp_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpSegSmem)));
                     ctx->sp_attr_done = true;
@@ -1308,7 +1314,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_finish<true><<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
                 s.launched(9);
-                if (overlap && !ctx->no_hop) {
+                if (hops) {
                     // tables for segment hops over the chains that failed the verification; the walker (already running
                     // on the other stream) starts using them when the ready flag appears
                     if (!ctx->hop_attr_done) {
@@ -1322,7 +1328,12 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             }
             if (overlap) {
                 FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-                if (!ctx->no_hop) {
+            } else {
+                int wrc = launch_walk();
+                if (wrc) return wrc;
+            }
+            {
+                if (hops) {
                     StageScope s(ctx, ST_SPEC);
                     SpArgs sa;
                     sa.fine = L.fine; sa.blk_rec4 = (const uint4 *)L.blk_rec; sa.desc = L.sp_desc; sa.seg_desc = L.sp_seg_desc; sa.counts = L.sp_counts;
@@ -1331,9 +1342,6 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                     k_hop_finish<<<(L.spsz.max_seg + 3) / 4, 128, 0, st>>>(sa, L.hop);
                     s.launched(2);
                 }
-            } else {
-                int wrc = launch_walk();
-                if (wrc) return wrc;
             }
             {
                 StageScope s(ctx, ST_KFILL);

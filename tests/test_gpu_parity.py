@@ -254,3 +254,12 @@ def test_16bit_truncated(codec):
     with pytest.raises(felics_b200.DecompressionError) as e:
         codec.decompress(fel[: len(fel) // 2])
     assert e.value.kind == "IoError"
+
+
+def test_speculation_and_segment_hops_are_exercised(codec):
+    # one big stationary image: some chains resolve speculatively, rejected ones cross segments by hops, the rest is walked
+    img = gnat_image(2048, 2048)
+    check(codec, img)
+    cnt = codec.debug_counters()
+    assert cnt[3] >= 4 and 1 <= cnt[4] < cnt[3], cnt          # chains tried / resolved by the speculative walk
+    assert cnt[5] >= 1 and cnt[6] >= 1, cnt                   # hops taken and hops refused (flip inside the segment)

@@ -27,5 +27,5 @@ with felics_b200.Codec(0) as c:
         got = c.compress(img)
         st = c.stage_times()
         cnt = c.debug_counters()
-        print(f"{name}: {'OK' if got == want else 'MISMATCH'} bytes {len(got)} oracle {t1 - t0:.2f}s live {cnt[0]} flags {cnt[2]} sp tried {cnt[3]} resolved {cnt[4]} "
+        print(f"{name}: {'OK' if got == want else 'MISMATCH'} bytes {len(got)} oracle {t1 - t0:.2f}s live {cnt[0]} flags {cnt[2]} sp tried {cnt[3]} resolved {cnt[4]} hops {cnt[5]}/{cnt[5] + cnt[6]} "
               f"spec {st['spec'][0]:.3f} walk {st['walk'][0]:.3f} total {sum(v[0] for v in st.values()):.3f} ms", flush=True)
