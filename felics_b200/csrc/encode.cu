@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
         // segment hops (hop_walk.cuh): once the tables of a chain the speculation rejected are ready, a segment whose
         // entry state passes the threshold tests is crossed with one lookup instead of being walked
         bool hop_on = false;
-        uint32_t hop_seg0 = 0, hop_kb = 0, hop_skip = 0, hop_fails = 0, ready = 0, hops_done = 0, hops_refused = 0;
+        uint32_t hop_seg0 = 0, hop_kb = 0, kb_pref = 0, kb_pref_seg = 0xFFFFFFFFu, hop_skip = 0, hop_fails = 0, ready = 0, hops_done = 0, hops_refused = 0;
         bool abs_state = false; // after a hop the counters are held as plain values at the start of window w
         uint32_t S[NK] = {0, 0, 0, 0, 0, 0};
         uint32_t w = 0;         // next window to process
@@ -572,7 +572,6 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 if (di != 0xFFFFFFFFu && *reinterpret_cast<const volatile uint32_t *>(a.chain_fail + di) == SP_OK - 1) {
                     hop_on = true;
                     hop_seg0 = a.desc[di].seg0;
-                    hop_kb = a.desc[di].kb;
                     hop_skip = (w >> 2) + 1;   // first attempt at the next segment boundary
                 }
             }
@@ -588,10 +587,12 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 if (!abs_state) {
                     S[0] = base[0] + t0.x; S[1] = base[1] + t0.y; S[2] = base[2] + t0.z; S[3] = base[3] + t0.w; S[4] = base[4] + t1.x; S[5] = base[5] + t1.y;
                 }
+                const size_t slot = hop_seg0 + seg;
+                hop_kb = kb_pref_seg == seg ? kb_pref : a.hop.segkb[slot];      // the segment's own binding candidate
+                if ((seg + 1) * 4u < nwin) { kb_pref = a.hop.segkb[slot + 1]; kb_pref_seg = seg + 1; }   // in flight for the next attempt
                 uint32_t x = S[0], mine = S[0];
 #pragma unroll
                 for (uint32_t k = 1; k < NK; k++) { x = hop_kb == k ? S[k] : x; mine = lane == k ? S[k] : mine; }
-                const size_t slot = hop_seg0 + seg;
                 bool good = x >= 1u && x <= HALVE_AT;
                 uint32_t xn = 0, th = 0, dt = 0;
                 unsigned long long A = 0;
@@ -1125,6 +1126,7 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
         L.hop.theta = c.take<uint32_t>((size_t)z.max_seg * NK * 1024);
         L.hop.A = c.take<unsigned long long>((size_t)z.max_seg * NK * 1024);
         L.hop.dt = c.take<uint32_t>((size_t)z.max_seg * NK * 1024);
+        L.hop.segkb = c.take<uint32_t>(z.max_seg);
         L.hop.log = c.take<uint32_t>((size_t)z.max_seg * 8 + 8);   // + the ready flag
         L.hop.ready = L.hop.log ? L.hop.log + (size_t)z.max_seg * 8 : nullptr;
         L.hop.pc2desc = L.sp_pc2desc;

@@ -25,6 +25,7 @@ struct HopTables {
     unsigned long long *A;        // [seg slot][6][1024]
     uint32_t *dt;                 // [seg slot][6][1024]
     uint32_t *log;                // [seg slot][8]: entry values of the six counters, epochs recorded at entry, 1 = hopped
+    uint32_t *segkb;              // [seg slot]: the segment's own presumed binding counter (smallest cost inside the segment)
     uint32_t *ready;              // [0]: 1 once the tables are complete
     const uint32_t *pc2desc;      // [plane*512 + context] -> descriptor index (0xFFFFFFFF: none)
 };
@@ -43,7 +44,7 @@ __global__ void __launch_bounds__(1024, 1) k_hop_maps(SpArgs a, HopTables h) {
     const uint32_t di = a.seg_desc[slot];
     if (a.chain_fail[di] != SP_OK - 1) return;     // only chains that failed the verification
     const SpDesc d = a.desc[di];
-    const uint32_t seg = slot - d.seg0, kb = d.kb;
+    const uint32_t seg = slot - d.seg0;
     const uint32_t e0 = seg * SP_SEG;
     const uint32_t nel = min(d.count - e0, (uint32_t)SP_SEG);
     const uint32_t g0 = d.gbase + e0;
@@ -62,6 +63,17 @@ __global__ void __launch_bounds__(1024, 1) k_hop_maps(SpArgs a, HopTables h) {
         }
     }
     __syncthreads();
+    // the segment's own binding candidate: the counter with the smallest cost inside the segment (ties: larger k);
+    // natural images are not stationary, the chain-wide choice of the speculative walk is often wrong locally
+    uint32_t kb = 0;
+    {
+        uint32_t best = 0xffffffffu;
+        for (uint32_t k = 0; k < NK; k++) {
+            const uint32_t tot = S.T[nel * 8 + k];
+            if (tot <= best) { best = tot; kb = k; }
+        }
+    }
+    if (threadIdx.x == 0) h.segkb[slot] = kb;
 #pragma unroll
     for (int i = 0; i < SP_SEG / 1024; i++) {
         const uint32_t j = threadIdx.x + i * 1024u;
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(128) k_hop_emit(SpArgs a, HopTables h) {
     if (lg[7] != 1u) return;
     const uint32_t di = a.seg_desc[slot];
     const SpDesc d = a.desc[di];
-    const uint32_t seg = slot - d.seg0, kb = d.kb;
+    const uint32_t seg = slot - d.seg0, kb = h.segkb[slot];
     const uint32_t e0 = seg * SP_SEG;
     const uint32_t nel = min(d.count - e0, (uint32_t)SP_SEG);
     const uint32_t g0 = d.gbase + e0, b0 = g0 >> 5, nblk = (nel + 31u) >> 5;
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(128) k_hop_finish(SpArgs a, HopTables h) {
     const uint32_t e0 = seg * SP_SEG;
     const uint32_t nel = min(d.count - e0, (uint32_t)SP_SEG);
     const uint32_t g0 = d.gbase + e0;
-    const uint32_t x_in = lg[d.kb];
+    const uint32_t x_in = lg[h.segkb[slot]];
     const uint32_t n = h.xn[(size_t)slot * 1024 + (x_in - 1u)] >> 16;   // halvings inside the segment
     const uint32_t nep0 = lg[6];                                         // index of the first new epoch
     const uint4 s0 = a.blk_rec4[(size_t)(g0 >> 5) * 4], s1 = a.blk_rec4[(size_t)(g0 >> 5) * 4 + 1];

@@ -31,6 +31,9 @@ SMALL = {
     "image-suite/grayscale/8bit/boat.512.tiff": "gray8_boat.512",
     "image-suite/rgb/8bit/lena_color_256.tif": "rgb8_lena_color_256",
     "bench/tiff_files/pluto.tiff": "rgb8_pluto",
+    # larger natural images: mirror-tiled in the GPU tests they give long chains with real statistics
+    "image-suite/grayscale/8bit/5.3.01.tiff": "gray8_5.3.01",
+    "image-suite/rgb/8bit/mandril_color.tif": "rgb8_mandril",
 }
 
 

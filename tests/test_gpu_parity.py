@@ -263,3 +263,27 @@ def test_speculation_and_segment_hops_are_exercised(codec):
     cnt = codec.debug_counters()
     assert cnt[3] >= 4 and 1 <= cnt[4] < cnt[3], cnt          # chains tried / resolved by the speculative walk
     assert cnt[5] >= 1 and cnt[6] >= 1, cnt                   # hops taken and hops refused (flip inside the segment)
+
+
+# ---- natural statistics at larger sizes (configs[4]: "synthetic-resized" = mirror-tiled corpus images) ----
+def mirror_tile(img, ny, nx):
+    rows = [np.concatenate([img[:, ::-1] if (i + j) % 2 else img for j in range(nx)], axis=1) for i in range(ny)]
+    return np.ascontiguousarray(np.concatenate([r[::-1] if i % 2 else r for i, r in enumerate(rows)], axis=0))
+
+
+@pytest.mark.parametrize("name,file", [("gray8_5.3.01", "image-suite/grayscale/8bit/5.3.01.tiff"), ("rgb8_mandril", "image-suite/rgb/8bit/mandril_color.tif")])
+def test_golden_natural_images(codec, golden_images, corpus_manifest, name, file):
+    entry = next(e for e in corpus_manifest if e["file"] == file)
+    fel = check(codec, golden_images[name])
+    assert len(fel) == entry["fel_bytes"] and hashlib.sha256(fel).hexdigest() == entry["fel_sha256"]
+
+
+def test_natural_image_mirror_tiled(codec, golden_images):
+    # long chains with natural (non-stationary) statistics: speculation mostly rejected, hops and serial walk mixed
+    check(codec, mirror_tile(golden_images["gray8_5.3.01"], 2, 2))      # 2048 x 2048
+    check(codec, mirror_tile(golden_images["rgb8_mandril"], 2, 3))      # 1536 x 1024 RGB
+    big = mirror_tile(golden_images["gray8_5.3.01"], 3, 4)              # 4096 x 3072
+    got = codec.compress(big)
+    assert got == fo.compress(big)
+    cnt = codec.debug_counters()
+    assert cnt[2] == 0
