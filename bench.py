@@ -83,7 +83,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -93,6 +93,10 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
+
+    def mark(self):
+        """Samples taken from here on belong to the timed region."""
+        self.first = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -104,7 +108,9 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        first = getattr(self, "first", 0)
+        lines = self.lines[first:] if len(self.lines) > first else self.lines   # a very short timed region: fall back to the warm-up samples
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -297,6 +303,8 @@ def run_ours(args):
             ms.append(a.elapsed_time(b))
         return ms
 
+    sampler = ClockSampler(local)
+    sampler.start()   # nvidia-smi needs a moment to come up: start before the warm-up, count samples from the timed region on
     # warm-up (also sizes the scratch buffers)
     for _ in range(max(args.warmup, 1)):
         offsets = encode_device()
@@ -304,10 +312,9 @@ def run_ours(args):
         encode_host()
     fel_bytes = int(offsets[n_img])
 
-    sampler = ClockSampler(local)
     codec.profile(True)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     ms_dev = timed(encode_device, args.steps)
     wall_dev = time.perf_counter() - t_wall0

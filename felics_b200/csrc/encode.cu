@@ -1,17 +1,18 @@
-// FELICS encode pipeline for sm_100a.
+// FELICS encode pipeline for sm_100a (8-bit samples; 16-bit samples: encode16.cu).
 //
 // Replaces the reference's sequential compress_channel loop
 // (/root/reference/src/compression.rs:76-148) by data-parallel passes whose
 // output is byte-identical:
 //
-//   planes    pixels -> i16 planes (+ YCoCg-R, color_transform.rs:11-17)
+//   planes    RGB only: pixels -> Y/Co/Cg i16 planes (YCoCg-R, color_transform.rs:11-17); gray is read in place
 //   hist      per-tile histogram of out-of-range pixels by context
 //   chainscan / tilebase   counting-sort offsets: one "chain" per (plane, context)
 //   scatter   stable grouping of the residuals e by context (raster order kept)
-//   prefix    code cost of e under each k in {0..5} (rice_coding.rs:56-58), prefix-summed
-//   walk      KEstimator with count halving (parameter_selection.rs:49-85) recast as an
-//             "epoch walk": between two halvings the counters are S0 + prefix differences,
-//             so only the halving positions are found sequentially (one warp per chain)
+//   prefix    code cost of e under each k in {0..5} (rice_coding.rs:56-58), prefix-summed per 32-block / group / all
+//   spec      KEstimator with count halving (parameter_selection.rs:49-85) for long stationary chains: speculative
+//             parallel epoch walk, exact by verification (sp_walk.cuh), plus segment-hop tables (hop_walk.cuh)
+//   walk      the same recurrence walked epoch by epoch, one warp per chain (everything the speculation leaves),
+//             crossing flip-free segments of rejected chains with one table lookup; runs beside `spec` on a second stream
 //   kfill     k = argmin (ties to the largest k) for every out-of-range pixel, in parallel
 //   code      marker + phased-in / Rice code word and length per pixel
 //   bitscan   exclusive scans: tile -> plane -> image bit offsets (exact output size)
@@ -414,8 +415,6 @@ __global__ void __launch_bounds__(256) k_blkfinal(uint4 *__restrict__ blk_rec4, 
 // base[k] = S[k] - T(cur)[k] (mod 2^32), T = global exclusive cost prefix, cur = first
 // element of the current epoch; the counters before element t are base + T(t).
 // Epoch i is recorded as (first element, base) for k_kfill.
-// Per window of 32 blocks (1024 elements) the fine records (16 KB) and block records (2 KB)
-// are prefetched into shared memory with cp.async, double buffered.
 // ------------------------------------------------------------------------------------
 struct WalkArgs {
     const uint4 *fine;      // per-element prefix records (FINE) ...
@@ -434,10 +433,6 @@ struct WalkArgs {
     const SpDesc *desc;
     const uint32_t *chain_fail;
 };
-
-__device__ __forceinline__ void unpack6(const uint4 &f, uint32_t U[NK]) {
-    U[0] = f.x & 0xffffu; U[1] = f.x >> 16; U[2] = f.y & 0xffffu; U[3] = f.y >> 16; U[4] = f.z & 0xffffu; U[5] = f.z >> 16;
-}
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -179,16 +179,6 @@ __device__ __forceinline__ uint32_t sp_build_segment(SpSegSmem &S, const SpDesc 
     return nel;
 }
 
-// next halving element at or after element p for a counter worth x before element p; returns nel if none
-__device__ __forceinline__ uint32_t sp_next_halving(const SpSegSmem &S, uint32_t nel, uint32_t p, uint32_t x) {
-    const uint32_t q = S.tk[p] + (HALVE_AT - x);      // need tk[j + 1] > q
-    if (q >= S.tk[nel]) return nel;
-    if (q < (uint32_t)SP_INV_CAP) return S.inv[q];
-    uint32_t lo = p, hi = nel - 1;                     // beyond the table: bisection
-    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (S.tk[mid + 1] > q) hi = mid; else lo = mid + 1; }
-    return lo;
-}
-
 // 1. segment maps: one block per segment, one thread per phase x
 __global__ void __launch_bounds__(1024) k_sp_maps(SpArgs a) {
     extern __shared__ __align__(16) unsigned char sp_smem[];
