@@ -288,8 +288,18 @@ __global__ void __launch_bounds__(PREFIX_THREADS) k_prefix(const uint16_t *__res
     }
     const uint32_t b01 = x01 - u01[7], b23 = x23 - u23[7], b45 = x45 - u45[7];
     if (FINE) {
+        // each thread holds 8 consecutive 16-byte records: transpose through shared memory (XOR swizzle against bank
+        // conflicts) so that every store instruction writes 512 contiguous bytes per warp
+        __shared__ uint4 stage[PREFIX_THREADS * 8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) fine[g + i] = make_uint4(u01[i] + b01, u23[i] + b23, u45[i] + b45, e[i]);
+        for (int i = 0; i < 8; i++) stage[threadIdx.x * 8 + (i ^ (threadIdx.x & 7))] = make_uint4(u01[i] + b01, u23[i] + b23, u45[i] + b45, e[i]);
+        __syncthreads();
+        uint4 *out = fine + ((size_t)p * cap + off);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t f = i * PREFIX_THREADS + threadIdx.x, tt = f >> 3, ii = f & 7u;
+            out[f] = stage[tt * 8 + (ii ^ (tt & 7u))];
+        }
     }
     if ((lane & 3u) == 3u) {                 // the last quarter holds the block's totals
         const uint32_t bi = threadIdx.x >> 2;
