@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
 // kfill: k = argmin (ties to the largest k, parameter_selection.rs:78-83) of the counters before every out-of-range
 // element.  One thread per eight consecutive elements (four threads per 32-block): the costs are re-derived from the
 // residuals and scanned over the block, the epoch bases come from the walk's records.
-__global__ void __launch_bounds__(256) k_kfill(const uint16_t *__restrict__ e_grp, const uint4 *__restrict__ blk_rec4,
+__global__ void __launch_bounds__(256, 4) k_kfill(const uint16_t *__restrict__ e_grp, const uint4 *__restrict__ blk_rec4,
                                                const uint32_t *__restrict__ blk_epoch, const uint4 *__restrict__ ep_rec,
                                                const uint32_t *__restrict__ plane_used, uint32_t cap, uint32_t np,
                                                uint8_t *__restrict__ k_grp) {
