@@ -138,6 +138,16 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->staging_in) cudaFree(ctx->staging_in);
     if (ctx->staging_out) cudaFree(ctx->staging_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_pack[i]) cudaEventDestroy(ctx->ev_pack[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+        if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
+        if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
+    }
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -222,6 +232,8 @@ int felics_compress_batch(felics_ctx *ctx, size_t n, const void *pixels, const f
     if (n == 0) return FELICS_OK;
     size_t in_bytes = felics_pixel_bytes(hdr) * n;
     if (in_bytes && !pixels) { set_error("null pixels"); return FELICS_ERR_INVALID_ARGUMENT; }
+    // 8-bit samples: sub-batches stream through the device (copy in / encode / copy out overlap)
+    if (hdr->pixel_depth == 0) return encode_batch_device(ctx, n, nullptr, *hdr, nullptr, arena, arena_cap, offsets, pixels ? pixels : (const void *)arena);
     if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, in_bytes + 16))) return rc;
     if (in_bytes) FELICS_CUDA_TRY(cudaMemcpyAsync(ctx->staging_in, pixels, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     return encode_batch_device(ctx, n, ctx->staging_in, *hdr, nullptr, arena, arena_cap, offsets);

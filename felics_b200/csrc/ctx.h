@@ -49,6 +49,13 @@ struct felics_ctx {
     size_t staging_in_cap = 0;
     void *staging_out = nullptr;
     size_t staging_out_cap = 0;
+    // host-memory batches: sub-batches are copied in, encoded and copied out on three streams (double buffered)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_pack[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    void *stage_in[2] = {nullptr, nullptr};
+    size_t stage_in_cap[2] = {0, 0};
+    void *stage_out[2] = {nullptr, nullptr};
+    size_t stage_out_cap[2] = {0, 0};
     void *pinned = nullptr;       // small pinned host buffer for read-backs
     size_t pinned_cap = 0;
 
@@ -100,7 +107,7 @@ int profile_collect(felics_ctx *ctx);  // after a stream sync: fold pending even
 
 // encode.cu
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
-                        uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
+                        uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels = nullptr);
 // encode16.cu: 16-bit samples
 int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                           uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);

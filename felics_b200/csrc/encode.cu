@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 }
                 hop_fails++;
                 hops_refused++;
-                hop_skip = seg + 1 + (hop_fails >= 2 ? min(1u << (hop_fails - 2), 64u) : 0u);
+                hop_skip = seg + 1 + (hop_fails >= 2 ? (1u << min(hop_fails - 2u, 6u)) : 0u);   // back off: 1, 2, 4, .. 64 segments
             }
             // ---- stream mode: walk window w element-exactly ----
             {
@@ -1146,8 +1146,10 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
 
 // Exactly one of d_arena (device memory, 4-byte aligned) / h_arena (host memory) is non-null.
 // With h_arena every sub-batch is packed into the context's staging buffer and copied out.
+// With h_pixels (host memory in, host arena out) the sub-batches are double buffered: the copy-in of sub-batch i+1 and the
+// copy-out of sub-batch i-1 run on their own streams beside the kernels of sub-batch i.
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena,
-                        uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host) {
+                        uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels) {
     if (hdr.pixel_depth != 0) return encode16_batch_device(ctx, n, d_pixels, hdr, d_arena, h_arena, arena_cap, offsets_host);
     if (d_arena && ((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
@@ -1179,17 +1181,67 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
         set_error("image too large for one call");
         return FELICS_ERR_INVALID_DIMENSIONS;
     }
+    const bool piped = h_pixels != nullptr;
+    if (!d_arena && !piped) {
+        set_error("a host arena needs host pixels (the pipelined path)");
+        return FELICS_ERR_INVALID_ARGUMENT;
+    }
+    // copies of earlier sub-batches may still be writing the caller's arena: finish them before any early return
+    auto drain = [&]() {
+        if (piped && ctx->copy_in) { cudaStreamSynchronize(ctx->copy_in); cudaStreamSynchronize(ctx->copy_out); }
+    };
+    if (piped) {
+        if (n >= 64) sub = std::min(sub, std::max<size_t>(32, (n + 7) / 8));   // at least eight sub-batches to overlap
+        if (!ctx->copy_in) {
+            FELICS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+            FELICS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) {
+                FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+                FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+                FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_pack[i], cudaEventDisableTiming));
+                FELICS_CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+            }
+        }
+    }
+    // copy sub-batch `idx` (images first .. first+ni) into its staging slot, after the kernels that last read the slot
+    auto enqueue_in = [&](size_t idx, size_t first, size_t ni) -> int {
+        const int slot = (int)(idx & 1);
+        const size_t bytes = ni * img_pix_bytes;
+        int rc2 = ensure_buffer(ctx, &ctx->stage_in[slot], &ctx->stage_in_cap[slot], bytes + 16);
+        if (rc2) return rc2;
+        FELICS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[slot], 0));
+        if (bytes) FELICS_CUDA_TRY(cudaMemcpyAsync(ctx->stage_in[slot], (const uint8_t *)h_pixels + first * img_pix_bytes, bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_in[slot], ctx->copy_in));
+        return FELICS_OK;
+    };
+    if (piped) {
+        // the copy streams start after whatever the caller queued on the context's stream
+        FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_done[0], st));
+        FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_done[1], st));
+        int rc0 = enqueue_in(0, 0, std::min(sub, n));
+        if (rc0) return rc0;
+    }
 
     uint64_t arena_off = 0;
     offsets_host[0] = 0;
-    for (size_t first = 0; first < n; first += sub) {
+    size_t idx = 0;
+    for (size_t first = 0; first < n; first += sub, idx++) {
         const size_t ni = std::min(sub, n - first);
         const size_t np = ni * g.nch;
+        const int slot = (int)(idx & 1);
         Layout L = carve(nullptr, g, ni);
         int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, L.bytes);
         if (rc) return rc;
         L = carve((uint8_t *)ctx->scratch, g, ni);
         const uint8_t *px = (const uint8_t *)d_pixels + first * img_pix_bytes;
+        if (piped) {
+            if (first + sub < n) {   // the next sub-batch's pixels travel while this one is encoded
+                rc = enqueue_in(idx + 1, first + sub, std::min(sub, n - first - sub));
+                if (rc) return rc;
+            }
+            FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_in[slot], 0));
+            px = (const uint8_t *)ctx->stage_in[slot];
+        }
 
         // gray samples are classified straight from the caller's pixels; RGB goes through Y/Co/Cg planes
         const bool gray = g.nch == 1;
@@ -1387,6 +1439,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
         FELICS_CUDA_TRY(cudaStreamSynchronize(st));
         for (int i = 0; i < 8; i++) ctx->dbg_counters[i] = h_cnt[i];
         if (h_cnt[2]) {
+            drain();
             set_error("internal: epoch record capacity exceeded (flags %u)", h_cnt[2]);
             return FELICS_ERR_CUDA;
         }
@@ -1397,16 +1450,18 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             arena_off += sub_total;
             for (size_t f2 = first + ni; f2 < n; f2++) offsets_host[f2 + 1] = arena_off;  // lower bound only
             offsets_host[n] = arena_off;
+            drain();
             set_error("output capacity %zu too small (need at least %llu)", arena_cap, (unsigned long long)arena_off);
             return FELICS_ERR_BUFFER_TOO_SMALL;
         }
         uint8_t *target = d_arena;
         uint64_t target_off = arena_off;
         if (!d_arena) {
-            rc = ensure_buffer(ctx, &ctx->staging_out, &ctx->staging_out_cap, sub_total + 16);
+            rc = ensure_buffer(ctx, &ctx->stage_out[slot], &ctx->stage_out_cap[slot], sub_total + 16);
             if (rc) return rc;
-            target = (uint8_t *)ctx->staging_out;
+            target = (uint8_t *)ctx->stage_out[slot];
             target_off = 0;
+            FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out[slot], 0));   // the copy-out that last used this slot
         }
         {
             StageScope s(ctx, ST_PACK);
@@ -1422,15 +1477,24 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             else k_heads<int16_t><<<(unsigned)((np + 127) / 128), 128, 0, st>>>(pa, L.planes, (uint32_t)np, g.w, g.h, hdr.color_type, hdr.pixel_depth);
             s.launched();
         }
+        if (piped) FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_done[slot], st));   // the staged pixels are free again
         if (!d_arena) {
-            FELICS_CUDA_TRY(cudaMemcpyAsync(h_arena + arena_off, target, sub_total, cudaMemcpyDeviceToHost, st));
-            FELICS_CUDA_TRY(cudaStreamSynchronize(st));   // staging_out is reused by the next sub-batch
+            FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_pack[slot], st));
+            FELICS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_pack[slot], 0));
+            FELICS_CUDA_TRY(cudaMemcpyAsync(h_arena + arena_off, target, sub_total, cudaMemcpyDeviceToHost, ctx->copy_out));
+            FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_out[slot], ctx->copy_out));
         }
         ctx->dbg_rec = L.rec;
         ctx->dbg_rec_count = np * (size_t)g.npix;
         arena_off += sub_total;
     }
     FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+    if (piped) {
+        FELICS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_out));
+        // later work on the context's stream is ordered after the copies as well
+        FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out[0], 0));
+        FELICS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_out[1], 0));
+    }
     FELICS_CUDA_TRY(cudaGetLastError());
     return profile_collect(ctx);
 }

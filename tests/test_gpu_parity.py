@@ -287,3 +287,24 @@ def test_natural_image_mirror_tiled(codec, golden_images):
     assert got == fo.compress(big)
     cnt = codec.debug_counters()
     assert cnt[2] == 0
+
+
+def test_batch_streams_through_sub_batches(codec):
+    # 150 images from host memory: five sub-batches, copy-in / encode / copy-out double buffered on three streams
+    rng = np.random.default_rng(17)
+    imgs = np.stack([np.clip(gnat_image(48, 40, seed=s) + rng.integers(-3, 4, (40, 48)), 0, 255).astype(np.uint8) for s in range(150)])
+    arena, offsets = codec.compress_batch(imgs)
+    assert len(offsets) == 151 and int(offsets[150]) == len(arena)
+    for i in (0, 1, 31, 32, 33, 63, 64, 95, 96, 127, 128, 149):
+        assert arena[int(offsets[i]):int(offsets[i + 1])].tobytes() == fo.compress(imgs[i]), f"image {i}"
+    hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, 48, 40)
+    out, status = codec.decompress_batch(arena, offsets, hdr)
+    assert not status.any() and np.array_equal(out, imgs)
+    # too small an arena reports the size it needs and leaves no copy in flight
+    lib = felics_b200.load_library()
+    import ctypes as C
+    small = np.empty(1000, np.uint8)
+    offs = np.zeros(151, np.uint64)
+    chdr = felics_b200._c_header(hdr)
+    rc = lib.felics_compress_batch(codec._h, 150, imgs.ctypes.data, C.byref(chdr), small.ctypes.data, small.size, offs.ctypes.data_as(C.POINTER(C.c_uint64)))
+    assert rc == -8 and int(offs[150]) >= 1000
