@@ -194,47 +194,33 @@ constexpr uint32_t DEC_MAX_W = 32768;
 struct BitWindow {
     const uint32_t *words;
     uint64_t nwords;
-    uint64_t wi;          // next word to feed into the window
+    uint64_t wi;          // index of the word held in n0
     uint64_t win;         // unread bits, MSB first
     int navail;           // valid bits in win
     uint64_t used, limit; // bits consumed so far / bits in the file after the header
-    uint32_t c[4], nx[4]; // current group of 4 words and the prefetched next group (already byte-swapped)
+    uint32_t n0, n1;      // the next two words of the stream, loaded (and byte-swapped) well before they are needed
 
     __device__ __forceinline__ uint32_t load(uint64_t i) const { return i < nwords ? bswap32(__ldg(words + i)) : 0u; }
-    __device__ __forceinline__ void load_group(uint32_t g[4], uint64_t first) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) g[i] = load(first + i);
-    }
     __device__ __forceinline__ void init(const uint32_t *w, uint64_t nw, uint64_t bitpos, uint64_t bitend) {
         words = w; nwords = nw; used = 0; limit = bitend - bitpos;
         wi = bitpos >> 5;
         const uint32_t sh = (uint32_t)(bitpos & 31);
-        const uint64_t g0 = wi & ~3ull;
-        load_group(c, g0);
-        load_group(nx, g0 + 4);
-        win = 0; navail = 0;
-        const uint32_t first = next_word();
+        const uint32_t first = load(wi);
+        wi++;
+        n0 = load(wi);
+        n1 = load(wi + 1);
         win = (uint64_t)(first << sh) << 32;
         navail = 32 - (int)sh;
         refill();
     }
-    __device__ __forceinline__ uint32_t next_word() {
-        const uint32_t idx = (uint32_t)(wi & 3);
-        uint32_t v = c[0];
-        v = idx == 1 ? c[1] : v; v = idx == 2 ? c[2] : v; v = idx == 3 ? c[3] : v;
-        wi++;
-        if ((wi & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) c[i] = nx[i];
-            load_group(nx, wi + 4);
-        }
-        return v;
-    }
-    // keep more than 32 valid bits in the window
+    // keep more than 32 valid bits in the window; the word consumed was requested two refills (>= 32 bits) ago
     __device__ __forceinline__ void refill() {
         if (navail <= 32) {
-            win |= (uint64_t)next_word() << (32 - navail);
+            win |= (uint64_t)n0 << (32 - navail);
             navail += 32;
+            n0 = n1;
+            wi++;
+            n1 = load(wi + 1);
         }
     }
     __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(win >> 32); }
@@ -303,21 +289,25 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
             int16_t *cur = rows + (size_t)(y & 1u) * w;
             const int16_t *up = rows + (size_t)((y & 1u) ^ 1u) * w;
             if (lane == 0) {
+                // neighbours (misc.rs:6-24) without a per-pixel case split: inside a row v1 is the previous sample and
+                // v2 = upp[x]; `upp` is the row above, or this row shifted by two on the first row (i-1, i-2); the
+                // first sample of a row takes (v1, v2) = (left, b0): up / up-up, or up / up-right on the second row
                 uint32_t x = 0;
-                int left = 0, left2 = 0;
+                int left = 0, b0 = 0;
+                const int16_t *upp = up;
                 if (y == 0) {
                     cur[0] = (int16_t)p1; left = p1;
                     x = 1;
-                    if (w >= 2) { cur[1] = (int16_t)p2; left2 = p1; left = p2; x = 2; }
-                } else if (y == 1 && w == 1) {
-                    cur[0] = (int16_t)p2; x = 1;          // 1-wide image: the second raw sample is (0, 1)
+                    if (w >= 2) { cur[1] = (int16_t)p2; left = p2; x = 2; }
+                    upp = cur - 2;
+                } else if (y == 1) {
+                    if (w == 1) { cur[0] = (int16_t)p2; x = 1; }     // 1-wide image: the second raw sample is (0, 1)
+                    else { left = up[0]; b0 = up[1]; }
+                } else {
+                    left = col0_a; b0 = col0_b;
                 }
                 for (; x < w; x++) {
-                    int v1, v2;
-                    if (x > 0 && y > 0) { v1 = left; v2 = up[x]; }              // left, up
-                    else if (y == 0) { v1 = left; v2 = left2; }                 // first row: i-1, i-2
-                    else if (y >= 2) { v1 = col0_a; v2 = col0_b; }              // first column: up, up-up
-                    else { v1 = up[0]; v2 = up[1]; }                            // (0,1): up, up-right
+                    const int v1 = left, v2 = x == 0 ? b0 : upp[x];
                     const int hi = max(v1, v2), lo = min(v1, v2);
                     const uint32_t ctx = (uint32_t)(hi - lo);
                     if (ctx > 510u) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
@@ -373,7 +363,6 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
                     }
                     if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
                     cur[x] = (int16_t)value;
-                    left2 = left;
                     left = value;
                 }
                 if (br.eof()) st = FELICS_ERR_IO;   // the reference fails at the read that runs out of input, before any later check
