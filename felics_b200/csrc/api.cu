@@ -233,6 +233,7 @@ int felics_compress_batch(felics_ctx *ctx, size_t n, const void *pixels, const f
     size_t in_bytes = felics_pixel_bytes(hdr) * n;
     if (in_bytes && !pixels) { set_error("null pixels"); return FELICS_ERR_INVALID_ARGUMENT; }
     // 8-bit samples: sub-batches stream through the device (copy in / encode / copy out overlap)
+    // (images without pixels: any non-null host pointer selects the streaming path, nothing is read through it)
     if (hdr->pixel_depth == 0) return encode_batch_device(ctx, n, nullptr, *hdr, nullptr, arena, arena_cap, offsets, pixels ? pixels : (const void *)arena);
     if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, in_bytes + 16))) return rc;
     if (in_bytes) FELICS_CUDA_TRY(cudaMemcpyAsync(ctx->staging_in, pixels, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
