@@ -1,6 +1,7 @@
 """GPU check of the speculative epoch walk: parity against the oracle, counters, stage times."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import numpy as np
 import felics_b200
 from oracle import felics_oracle as fo
