@@ -308,3 +308,29 @@ def test_batch_streams_through_sub_batches(codec):
     chdr = felics_b200._c_header(hdr)
     rc = lib.felics_compress_batch(codec._h, 150, imgs.ctypes.data, C.byref(chdr), small.ctypes.data, small.size, offs.ctypes.data_as(C.POINTER(C.c_uint64)))
     assert rc == -8 and int(offs[150]) >= 1000
+
+
+# ---- randomised structure (hypothesis): shapes, dynamic range, smoothness, channel count ----
+def test_random_structured_images(codec):
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 300), st.integers(1, 120), st.booleans(), st.integers(0, 2**31 - 1), st.sampled_from([0, 1, 2, 5, 20, 128]),
+           st.sampled_from([1, 3, 17, 64]), st.sampled_from(["clip", "wrap", "binary"]))
+    def run(width, height, rgb, seed, noise, period, mode):
+        rng = np.random.default_rng(seed)
+        shape = (height, width, 3) if rgb else (height, width)
+        yy, xx = np.mgrid[0:height, 0:width]
+        base = 128 + 100 * np.sin(xx / period) * np.cos(yy / (period + 2.5))
+        if rgb:
+            base = np.stack([base, np.roll(base, 2, 1) * 0.7 + 30, 255 - base], axis=-1)
+        v = base + (rng.integers(-noise, noise + 1, shape) if noise else 0)
+        if mode == "clip":
+            img = np.clip(v, 0, 255)
+        elif mode == "wrap":
+            img = np.mod(v * 3, 256)
+        else:
+            img = (v > 128) * 255
+        check(codec, np.ascontiguousarray(img.astype(np.uint8)))
+
+    run()
