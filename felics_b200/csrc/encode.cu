@@ -973,39 +973,72 @@ __global__ void __launch_bounds__(TILE_THREADS) k_pack(PackArgs a) {
     if (in_smem)
         for (uint32_t j = threadIdx.x; j < nwords; j += TILE_THREADS) buf[j] = 0;
 
+    // a lane owns 16 consecutive pixels (four 16-byte loads): their codes are concatenated in registers and leave as
+    // whole words, so the shared-memory traffic is a few atomicOr per lane instead of one or two per pixel, and the
+    // bit offsets need one warp scan per 512 pixels
     const uint32_t *rc = a.rec + (size_t)p * a.npix;
-    uint32_t wstart = t * TILE + wid * WARP_PIX;
+    const uint32_t wstart = t * TILE + wid * WARP_PIX;
+    const uint32_t lstart = wstart + lane * WARP_ITERS;
     uint32_t r[WARP_ITERS];
-    uint32_t mysum = 0;
+    if (lstart + WARP_ITERS <= a.npix && (((size_t)p * a.npix + lstart) & 3u) == 0) {
+        const uint4 *r4 = reinterpret_cast<const uint4 *>(rc + lstart);
 #pragma unroll
-    for (int it = 0; it < WARP_ITERS; it++) {
-        uint32_t i = wstart + it * 32 + lane;
-        r[it] = i < a.npix ? rc[i] : 0u;
-        mysum += rec_len(r[it]);
+        for (int q = 0; q < WARP_ITERS / 4; q++) {
+            const uint4 v = r4[q];
+            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < WARP_ITERS; it++) r[it] = lstart + it < a.npix ? rc[lstart + it] : 0u;
     }
+    uint32_t mylen = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mysum += __shfl_xor_sync(0xffffffffu, mysum, o);
-    if (lane == 0) wtot[wid] = mysum;
+    for (int it = 0; it < WARP_ITERS; it++) mylen += rec_len(r[it]);
+    uint32_t inc = mylen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+    }
+    if (lane == 31) wtot[wid] = inc;
     __syncthreads();
-    uint32_t run = sh0;  // bit offset relative to word0
-    for (uint32_t q = 0; q < wid; q++) run += wtot[q];
+    uint32_t pos = sh0 + inc - mylen;  // bit offset of my first code relative to word0
+    for (uint32_t q = 0; q < wid; q++) pos += wtot[q];
 
     auto put_s = [&](uint64_t off, uint32_t val, int n) { put_bits_smem(buf, (uint32_t)off, val, n); };
     auto put_g = [&](uint64_t off, uint32_t val, int n) { put_bits_global(a.arena, (word0 << 5) + off, val, n); };
+    auto flush = [&](uint32_t w, uint32_t v) {
+        if (!v) return;
+        if (in_smem) atomicOr(&buf[w], v);
+        else atomicOr(&a.arena[word0 + w], bswap32(v));
+    };
+    uint32_t wi = pos >> 5, sh = pos & 31u, wv = 0;   // the word being filled: index, bits already placed in it, their value
 #pragma unroll
     for (int it = 0; it < WARP_ITERS; it++) {
-        uint32_t len = rec_len(r[it]);
-        uint32_t inc = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += n;
+        const uint32_t len = rec_len(r[it]);
+        if (len == 0) continue;
+        if (len <= (uint32_t)REC_SHORT_MAX) {
+            const uint32_t left = (r[it] & 0x3fffffu) << (32u - len);   // code word, MSB aligned
+            wv |= left >> sh;
+            if (sh + len >= 32u) {
+                flush(wi, wv);
+                wi++;
+                wv = sh + len > 32u ? left << (32u - sh) : 0u;         // sh > 0 here: len <= 22
+                sh = sh + len - 32u;
+            } else {
+                sh += len;
+            }
+        } else {
+            // long unary run: emitted field by field; my partial word goes out first
+            flush(wi, wv);
+            const uint32_t at = (wi << 5) + sh;
+            if (in_smem) emit_record(r[it], at, put_s);
+            else emit_record(r[it], at, put_g);
+            const uint32_t np2 = at + len;
+            wi = np2 >> 5; sh = np2 & 31u; wv = 0;
         }
-        uint32_t off = run + inc - len;
-        if (in_smem) emit_record(r[it], off, put_s);
-        else emit_record(r[it], off, put_g);
-        run += __shfl_sync(0xffffffffu, inc, 31);
     }
+    flush(wi, wv);
     if (!in_smem) return;
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < nwords; j += TILE_THREADS) {
