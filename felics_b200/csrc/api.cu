@@ -137,6 +137,7 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->staging_in) cudaFree(ctx->staging_in);
     if (ctx->staging_out) cudaFree(ctx->staging_out);
+    if (ctx->tables16) cudaFree(ctx->tables16);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);

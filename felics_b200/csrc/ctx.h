@@ -60,8 +60,12 @@ struct felics_ctx {
     size_t pinned_cap = 0;
 
     // per-context (hence per-device) one-time kernel attribute settings
-    bool walk_attr_done = false, sp_attr_done = false, hop_attr_done = false;
-    size_t decode_smem_set = 0;
+    bool walk_attr_done = false, sp_attr_done = false, hop_attr_done = false, enc16_attr_done = false, dec16_attr_done = false;
+    // 16-bit path: per-image estimator tables (tagged rows, serial16.cuh)
+    void *tables16 = nullptr;
+    size_t tables16_cap = 0;
+    uint32_t tag16 = 1;
+    size_t decode_smem_set = 0, dec16_smem_set = 0;
 
     bool prof = false;
     bool no_overlap = false;      // debug/profiling switch: run the serial walk after the speculative one, on the same stream
@@ -111,6 +115,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
 // encode16.cu: 16-bit samples
 int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                           uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
+int tables16(felics_ctx *ctx, size_t images, uint32_t **out);
+uint32_t next_tags16(felics_ctx *ctx);
 // decode.cu
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host);

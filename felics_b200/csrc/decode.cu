@@ -422,8 +422,11 @@ struct Dec16Args {
     const uint32_t *words;
     uint64_t arena_words;
     const uint64_t *offsets;
-    int32_t *planes;           // [n*nch][npix]
-    uint32_t *tables;          // [n][TABLE16_WORDS]
+    int32_t *planes;           // [n*nch][pstride]
+    size_t pstride;
+    uint32_t *tables;          // [n][TABLE16_WORDS], tagged rows (serial16.cuh)
+    uint32_t tag0;             // first tag of this call (one per channel)
+    uint32_t rows_smem;        // 1: two rows of samples fit in shared memory beside the estimator rows
     int *status;
     uint32_t w, h, npix, nch;
     uint8_t color, depth;
@@ -459,84 +462,117 @@ __global__ void __launch_bounds__(32) k16_decode(Dec16Args a, uint32_t n) {
 
     BitReader br;
     br.init(a.words, a.arena_words, 8 * (off0 + FELICS_HEADER_BYTES), 8 * off1);
-    uint32_t *tab = a.tables + (size_t)img * TABLE16_WORDS;
-    const uint32_t w = a.w;
+    extern __shared__ __align__(16) unsigned char dec16_smem[];
+    Est16 est;
+    est.sm = reinterpret_cast<uint32_t *>(dec16_smem);
+    est.gl = a.tables + (size_t)img * TABLE16_WORDS;
+    est.tag = 0;
+    // previous and current row in shared memory when they fit (a.rows_smem), else the neighbours come from the planes
+    int32_t *srow = reinterpret_cast<int32_t *>(dec16_smem + SM_TABLE16_BYTES);
+    const uint32_t w = a.w, h = a.h;
     for (uint32_t ch = 0; ch < a.nch && st == FELICS_OK; ch++) {
-        clear_table16(tab, lane);
+        est.reset(lane, a.tag0 + ch);
+        int32_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.pstride;
+        int32_t p1 = 0, p2 = 0;
         if (lane == 0) {
-            int32_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.npix;
-            const int32_t p1 = (int32_t)br.read(32), p2 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
+            p1 = (int32_t)br.read(32); p2 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
             if (br.eof) st = FELICS_ERR_IO;
-            else {
-                if (a.npix >= 1) pl[0] = p1;
-                if (a.npix >= 2) pl[1] = p2;
-            }
-            uint32_t x = 0, y = 0;
-            if (a.npix >= 3) { y = 2 / w; x = 2 - y * w; }
-            for (uint32_t i = 2; i < a.npix && st == FELICS_OK; i++) {
-                uint32_t ia, ib;
-                neighbours16(i, x, y, w, ia, ib);
-                const long long v1 = pl[ia], v2 = pl[ib];
-                const long long hi = max(v1, v2), lo = min(v1, v2);
-                if (hi - lo > (long long)MAXCTX16) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
-                const uint32_t ctx = (uint32_t)(hi - lo);
-                uint32_t *row = tab + (size_t)ctx * ROW16;
-                long long value;
-                if (br.read(1)) {                                       // InRange (:208-215)
-                    if (br.eof) { st = FELICS_ERR_IO; break; }
-                    const uint32_t nn = ctx + 1;
-                    const int m = 31 - __clz(nn);
-                    const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
-                    uint32_t xx = br.read((uint32_t)m);
-                    if (xx >= right_p) xx = (xx - right_p) * 2 + right_p + br.read(1);   // phase_in_coding.rs:102-109
-                    if (br.eof) { st = FELICS_ERR_IO; break; }
-                    xx += left_p;                                                        // rotate_left (:55-57)
-                    if (xx >= nn) xx -= nn;
-                    if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
-                    value = lo + (long long)xx;
-                } else {
-                    if (br.eof) { st = FELICS_ERR_IO; break; }
-                    const uint32_t above = br.read(1);
-                    const int k = get_k16(row);                            // get_k (:202)
-                    const uint32_t q = br.read_unary0();
-                    const uint32_t rem = br.read((uint32_t)k);
-                    if (br.eof) { st = FELICS_ERR_IO; break; }
-                    if (q > (1u << 20)) { st = FELICS_ERR_INVALID_VALUE; break; }
-                    const uint32_t e = (q << k) + rem;
-                    update16(row, e);
-                    value = above ? hi + (long long)e + 1 : lo - (long long)e - 1;   // (:216-243)
-                }
-                if (value < -2147483648ll || value > 2147483647ll) { st = FELICS_ERR_VALUE_OVERFLOW; break; }   // checked_add / checked_sub
-                pl[i] = (int32_t)value;
-                if (++x == w) { x = 0; y++; }
-            }
         }
         st = __shfl_sync(0xffffffffu, st, 0);
+        if (st != FELICS_OK || a.npix == 0) continue;
+        long long col0_a = 0, col0_b = 0;   // samples at x = 0 of the previous row and of the row before it
+        for (uint32_t y = 0; y < h && st == FELICS_OK; y++) {
+            int32_t *cur = a.rows_smem ? srow + (size_t)(y & 1u) * w : pl + (size_t)y * w;
+            const int32_t *up = a.rows_smem ? srow + (size_t)((y & 1u) ^ 1u) * w : pl + (size_t)(y ? y - 1 : 0) * w;   // unused on the first row
+            if (lane == 0) {
+                // neighbours (misc.rs:6-24) as in k_decode: v1 = previous sample, v2 = upp[x]; first sample of a row: (left, b0)
+                uint32_t x = 0;
+                long long left = 0, b0 = 0;
+                const int32_t *upp = up;
+                if (y == 0) {
+                    cur[0] = p1; left = p1;
+                    x = 1;
+                    if (w >= 2) { cur[1] = p2; left = p2; x = 2; }
+                    upp = cur - 2;
+                } else if (y == 1) {
+                    if (w == 1) { cur[0] = p2; x = 1; }
+                    else { left = up[0]; b0 = up[1]; }
+                } else {
+                    left = col0_a; b0 = col0_b;
+                }
+                for (; x < w; x++) {
+                    const long long v1 = left, v2 = x == 0 ? b0 : (long long)upp[x];
+                    const long long hi = max(v1, v2), lo = min(v1, v2);
+                    if (hi - lo > (long long)MAXCTX16) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
+                    const uint32_t ctx = (uint32_t)(hi - lo);
+                    long long value;
+                    if (br.read(1)) {                                       // InRange (:208-215)
+                        if (br.eof) { st = FELICS_ERR_IO; break; }
+                        const uint32_t nn = ctx + 1;
+                        const int m = 31 - __clz(nn);
+                        const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                        uint32_t xx = br.read((uint32_t)m);
+                        if (xx >= right_p) xx = (xx - right_p) * 2 + right_p + br.read(1);   // phase_in_coding.rs:102-109
+                        if (br.eof) { st = FELICS_ERR_IO; break; }
+                        xx += left_p;                                                        // rotate_left (:55-57)
+                        if (xx >= nn) xx -= nn;
+                        if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
+                        value = lo + (long long)xx;
+                    } else {
+                        if (br.eof) { st = FELICS_ERR_IO; break; }
+                        const uint32_t above = br.read(1);
+                        uint32_t cnt[NK16];
+                        est.load(ctx, cnt);
+                        const int k = get_k16(cnt);                         // get_k (:202)
+                        const uint32_t q = br.read_unary0();
+                        const uint32_t rem = br.read((uint32_t)k);
+                        if (br.eof) { st = FELICS_ERR_IO; break; }
+                        if (q > (1u << 20)) { st = FELICS_ERR_INVALID_VALUE; break; }
+                        const uint32_t e = (q << k) + rem;
+                        update16(cnt, e);
+                        est.store(ctx, cnt);
+                        value = above ? hi + (long long)e + 1 : lo - (long long)e - 1;   // (:216-243)
+                    }
+                    if (value < -2147483648ll || value > 2147483647ll) { st = FELICS_ERR_VALUE_OVERFLOW; break; }   // checked_add / checked_sub
+                    cur[x] = (int32_t)value;
+                    left = value;
+                }
+                col0_b = col0_a;
+                col0_a = cur[0];
+            }
+            st = __shfl_sync(0xffffffffu, st, 0);
+            __syncwarp();
+            if (a.rows_smem && st == FELICS_OK) {
+                int32_t *dst = pl + (size_t)y * w;
+                for (uint32_t x = lane; x < w; x += 32) dst[x] = cur[x];
+            }
+            __syncwarp();
+        }
     }
     if (lane == 0) a.status[img] = st;
 }
 
 // i32 planes -> u16 pixels with the try_into range checks (compression.rs:305-310, :402-407)
-__global__ void k16_unplane_gray(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t total, int *__restrict__ status) {
+__global__ void k16_unplane_gray(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t pstride, size_t total, int *__restrict__ status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         const size_t img = i / npix;
         if (status[img] != FELICS_OK) continue;
-        const int v = planes[i];
+        const int v = planes[img * pstride + (i - img * npix)];
         if (v < 0 || v > 65535) { atomicCAS(&status[img], FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
         px[i] = (uint16_t)v;
     }
 }
-__global__ void k16_unplane_rgb(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t total, int *__restrict__ status) {
+__global__ void k16_unplane_rgb(const int32_t *__restrict__ planes, uint16_t *__restrict__ px, uint32_t npix, size_t pstride, size_t total, int *__restrict__ status) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; idx < total; idx += stride) {
         const size_t img = idx / npix;
         if (status[img] != FELICS_OK) continue;
         const uint32_t i = (uint32_t)(idx - img * npix);
-        const int32_t *base = planes + img * 3 * (size_t)npix;
-        const long long y = base[i], co = base[(size_t)npix + i], cg = base[2 * (size_t)npix + i];
+        const int32_t *base = planes + img * 3 * pstride;
+        const long long y = base[i], co = base[pstride + i], cg = base[2 * pstride + i];
         const long long t = y - cg / 2;      // color_transform.rs:20-26
         const long long g = cg + t;
         const long long b = t - co / 2;
@@ -554,15 +590,23 @@ static int decode16_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_are
     const size_t sub = std::max<size_t>(1, std::min<size_t>(n, 64));
     size_t off_bytes = align_up((n + 1) * sizeof(uint64_t), 256);
     size_t stat_bytes = align_up(n * sizeof(int), 256);
-    size_t plane_bytes = align_up((sub * nch * (size_t)npix + 8) * sizeof(int32_t), 256);
-    size_t table_bytes = align_up(sub * TABLE16_WORDS * sizeof(uint32_t), 256);
-    int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off_bytes + stat_bytes + plane_bytes + table_bytes);
+    const size_t pstride = plane_stride16(npix);
+    size_t plane_bytes = align_up((sub * nch * pstride + 8) * sizeof(int32_t), 256);
+    int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off_bytes + stat_bytes + plane_bytes);
     if (rc) return rc;
+    uint32_t *d_tables = nullptr;
+    if ((rc = tables16(ctx, sub, &d_tables))) return rc;
+    const size_t row_bytes = 2 * (size_t)hdr.width * sizeof(int32_t);
+    const bool rows_smem = SM_TABLE16_BYTES + row_bytes <= (size_t)200 * 1024;
+    const size_t smem = SM_TABLE16_BYTES + (rows_smem ? row_bytes : 0);
+    if (smem > ctx->dec16_smem_set) {
+        FELICS_CUDA_TRY(cudaFuncSetAttribute(k16_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->dec16_smem_set = smem;
+    }
     uint8_t *sb = (uint8_t *)ctx->scratch;
     uint64_t *d_off = (uint64_t *)sb;
     int *d_status = (int *)(sb + off_bytes);
     int32_t *d_planes = (int32_t *)(sb + off_bytes + stat_bytes);
-    uint32_t *d_tables = (uint32_t *)(sb + off_bytes + stat_bytes + plane_bytes);
     FELICS_CUDA_TRY(cudaMemcpyAsync(d_off, offsets_host, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     const size_t img_bytes = (size_t)npix * nch * 2;
     for (size_t first = 0; first < n; first += sub) {
@@ -570,11 +614,13 @@ static int decode16_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_are
         Dec16Args a;
         a.words = (const uint32_t *)d_arena;
         a.arena_words = (offsets_host[n] + 3) / 4;
-        a.offsets = d_off + first; a.planes = d_planes; a.tables = d_tables; a.status = d_status + first;
+        a.offsets = d_off + first; a.planes = d_planes; a.pstride = pstride; a.tables = d_tables; a.status = d_status + first;
         a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch; a.color = hdr.color_type; a.depth = hdr.pixel_depth;
         {
             StageScope s(ctx, ST_DECODE);
-            k16_decode<<<(unsigned)ni, 32, 0, st>>>(a, (uint32_t)ni);
+            a.tag0 = next_tags16(ctx);
+            a.rows_smem = rows_smem ? 1u : 0u;
+            k16_decode<<<(unsigned)ni, 32, smem, st>>>(a, (uint32_t)ni);
             s.launched();
         }
         if (npix > 0) {
@@ -582,8 +628,8 @@ static int decode16_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_are
             const size_t total = ni * (size_t)npix;
             const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
             uint16_t *out = (uint16_t *)((uint8_t *)d_pixels_out + first * img_bytes);
-            if (nch == 1) k16_unplane_gray<<<blocks, 256, 0, st>>>(d_planes, out, npix, total, d_status + first);
-            else k16_unplane_rgb<<<blocks, 256, 0, st>>>(d_planes, out, npix, total, d_status + first);
+            if (nch == 1) k16_unplane_gray<<<blocks, 256, 0, st>>>(d_planes, out, npix, pstride, total, d_status + first);
+            else k16_unplane_rgb<<<blocks, 256, 0, st>>>(d_planes, out, npix, pstride, total, d_status + first);
             s.launched();
         }
     }
