@@ -18,7 +18,8 @@ struct DecArgs {
     const uint32_t *words;     // the arena viewed as 32-bit words (4-byte aligned)
     uint64_t arena_words;      // number of whole words that may be read
     const uint64_t *offsets;   // device copy, n+1 entries (bytes)
-    int16_t *planes;           // [n*nch][npix]
+    int16_t *planes;           // [n*nch][pstride]: padded, see plane_stride8
+    size_t pstride;
     int *status;               // [n]
     uint32_t w, h, npix, nch;
     uint8_t color, depth;
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
         for (uint32_t j = lane; j < (NBIN - 1) * NK; j += 32) tab[j] = 0;   // fresh estimator per channel (:186-190)
         __syncwarp();
         if (lane == 0) {
-            int16_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.npix;
+            int16_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.pstride;
             int32_t p1 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
             int32_t p2 = (int32_t)br.read(32);
             if (br.eof) st = FELICS_ERR_IO;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
     for (uint32_t ch = 0; ch < a.nch && st == FELICS_OK; ch++) {
         for (uint32_t j = lane; j < (NBIN - 1) * NK; j += 32) tab[j] = 0;   // fresh estimator per channel (:186-190)
         __syncwarp();
-        int16_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.npix;
+        int16_t *pl = a.planes + ((size_t)img * a.nch + ch) * a.pstride;
         int32_t p1 = 0, p2 = 0;
         if (lane == 0) {
             p1 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
@@ -382,21 +383,25 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
 }
 
 // planes -> pixels with the try_into range checks (compression.rs:305-310, :402-407)
-__global__ void k_unplane_gray8(const int16_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, size_t total,
+// distance between consecutive planes, in samples.  One warp per file writes its rows in lockstep with the others:
+// a power-of-two distance would put every file's stores on the same memory channel.
+inline size_t plane_stride8(uint32_t npix) { return (size_t)npix + 4672; }
+
+__global__ void k_unplane_gray8(const int16_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, size_t pstride, size_t total,
                                 int *__restrict__ status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         size_t img = i / npix;
         if (status[img] != FELICS_OK) continue;
-        int v = planes[i];
+        int v = planes[img * pstride + (i - img * npix)];
         if (v < 0 || v > 255) { atomicCAS(&status[img], FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
         px[i] = (uint8_t)v;
     }
 }
 
 // color_transform.rs:20-26
-__global__ void k_unplane_rgb8(const int16_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, size_t total,
+__global__ void k_unplane_rgb8(const int16_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, size_t pstride, size_t total,
                                int *__restrict__ status) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -404,8 +409,8 @@ __global__ void k_unplane_rgb8(const int16_t *__restrict__ planes, uint8_t *__re
         size_t img = idx / npix;
         if (status[img] != FELICS_OK) continue;
         uint32_t i = (uint32_t)(idx - img * npix);
-        const int16_t *base = planes + img * 3 * (size_t)npix;
-        int y = base[i], co = base[(size_t)npix + i], cg = base[2 * (size_t)npix + i];
+        const int16_t *base = planes + img * 3 * pstride;
+        int y = base[i], co = base[pstride + i], cg = base[2 * pstride + i];
         int t = y - cg / 2;
         int g = cg + t;
         int b = t - co / 2;
@@ -659,7 +664,8 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
 
     size_t off_bytes = align_up((n + 1) * sizeof(uint64_t), 256);
     size_t stat_bytes = align_up(n * sizeof(int), 256);
-    size_t plane_bytes = align_up(((size_t)n * nch * npix + 8) * sizeof(int16_t), 256);
+    const size_t pstride = plane_stride8(npix);
+    size_t plane_bytes = align_up(((size_t)n * nch * pstride + 8) * sizeof(int16_t), 256);
     int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off_bytes + stat_bytes + plane_bytes);
     if (rc) return rc;
     uint8_t *sb = (uint8_t *)ctx->scratch;
@@ -672,7 +678,7 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     a.words = (const uint32_t *)d_arena;
     a.arena_words = (offsets_host[n] + 3) / 4;   // the word holding the last byte must be readable
     a.offsets = d_off; a.planes = d_planes; a.status = d_status;
-    a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch;
+    a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch; a.pstride = pstride;
     a.color = hdr.color_type; a.depth = hdr.pixel_depth;
     {
         StageScope s(ctx, ST_DECODE);
@@ -692,8 +698,8 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
         StageScope s(ctx, ST_UNPLANE);
         size_t total = n * (size_t)npix;
         unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
-        if (nch == 1) k_unplane_gray8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)d_pixels_out, npix, total, d_status);
-        else k_unplane_rgb8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)d_pixels_out, npix, total, d_status);
+        if (nch == 1) k_unplane_gray8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)d_pixels_out, npix, pstride, total, d_status);
+        else k_unplane_rgb8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)d_pixels_out, npix, pstride, total, d_status);
         s.launched();
     }
     FELICS_CUDA_TRY(cudaMemcpyAsync(status_host, d_status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
