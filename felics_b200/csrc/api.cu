@@ -116,6 +116,10 @@ int felics_ctx_create(int device, felics_ctx **out) {
     {
         const char *ns = getenv("FELICS_B200_NO_SPEC");   // debug switch: force the serial epoch walk
         ctx->no_spec = ns && ns[0] == '1';
+        const char *s16 = getenv("FELICS_B200_SERIAL16");   // debug switch: serial 16-bit encoder
+        ctx->serial16 = s16 && s16[0] == '1';
+        const char *bw = getenv("FELICS_B200_BW16");
+        ctx->bw16_opts = bw ? (uint32_t)strtoul(bw, nullptr, 0) : 0u;
         const char *no = getenv("FELICS_B200_NO_OVERLAP");   // profiling switch: one stream, kernels back to back
         ctx->no_overlap = no && no[0] == '1';
         const char *nh = getenv("FELICS_B200_NO_HOP");       // debug switch: no segment hops

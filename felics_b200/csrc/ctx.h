@@ -71,6 +71,8 @@ struct felics_ctx {
     bool no_overlap = false;      // debug/profiling switch: run the serial walk after the speculative one, on the same stream
     bool no_hop = false;          // debug switch: no segment hops in the serial walker
     bool no_spec = false;         // debug/bench switch: skip the speculative walk
+    uint32_t bw16_opts = 0;       // experiment switches of the 16-bit bucket walk (FELICS_B200_BW16)
+    bool serial16 = false;        // debug switch: the one-warp-per-image 16-bit encoder instead of the parallel one
     std::vector<felics::ProfEntry> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     double stage_ms[felics::ST_COUNT] = {0};
@@ -115,6 +117,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
 // encode16.cu: 16-bit samples
 int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                           uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
+int encode16_serial_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
+                                 uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
 int tables16(felics_ctx *ctx, size_t images, uint32_t **out);
 uint32_t next_tags16(felics_ctx *ctx);
 // decode.cu

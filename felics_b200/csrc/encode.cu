@@ -19,6 +19,7 @@
 //   pack      MSB-first bit packing, identical to bitstream-io's BigEndian BitWriter
 #include "ctx.h"
 #include "device_common.cuh"
+#include "serial16.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist(const T *__restrict__ pla
     for (int j = 0; j < TILE / TILE_THREADS; j++) {
         if (cur.i >= 2 && cur.i < npix) {
             PixelClass pc = cur.classify();
-            if (pc.cls != 0) atomicAdd(&h[pc.delta], 1u);
+            if (pc.cls != 0) atomicAdd(&h[sizeof(T) == 4 ? (pc.delta & (NBIN - 1)) : pc.delta], 1u);   // 16-bit samples: buckets (enc16_par.cuh)
         }
         cur.step(TILE_THREADS);
     }
@@ -1177,17 +1178,21 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
 
 }  // namespace
 
+}  // namespace felics
+#include "enc16_par.cuh"
+namespace felics {
+
 // Exactly one of d_arena (device memory, 4-byte aligned) / h_arena (host memory) is non-null.
 // With h_arena every sub-batch is packed into the context's staging buffer and copied out.
 // With h_pixels (host memory in, host arena out) the sub-batches are double buffered: the copy-in of sub-batch i+1 and the
 // copy-out of sub-batch i-1 run on their own streams beside the kernels of sub-batch i.
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena,
                         uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels) {
-    if (hdr.pixel_depth != 0) return encode16_batch_device(ctx, n, d_pixels, hdr, d_arena, h_arena, arena_cap, offsets_host);
     if (d_arena && ((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;
     }
+    if (hdr.pixel_depth != 0) return encode16_batch_device(ctx, n, d_pixels, hdr, d_arena, h_arena, arena_cap, offsets_host);
     uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
     if (npix64 > 0x7fff0000ull) {
         set_error("image too large for one call: %llu pixels", (unsigned long long)npix64);

@@ -1,4 +1,5 @@
-// FELICS encode of 16-bit samples (see serial16.cuh): size pass, then a write pass at exact offsets.
+// Serial FELICS encode of 16-bit samples (see serial16.cuh): size pass, then a write pass at exact offsets.
+// Kept behind FELICS_B200_SERIAL16=1 as a cross-check of the parallel path (enc16_par.cuh); also home of the decoder's tables.
 #include "ctx.h"
 #include "device_common.cuh"
 #include "serial16.cuh"
@@ -157,7 +158,7 @@ uint32_t next_tags16(felics_ctx *ctx) {
     return t;
 }
 
-int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena, uint8_t *h_arena,
+int encode16_serial_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena, uint8_t *h_arena,
                           size_t arena_cap, uint64_t *offsets_host) {
     const uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
     if (npix64 > 0x7fff0000ull) {

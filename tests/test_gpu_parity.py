@@ -248,6 +248,66 @@ def test_batch_16bit(codec):
     assert not status.any() and np.array_equal(out, imgs)
 
 
+def gnat16(width, height, sigma, seed=2, amp=9000.0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    v = 30000 + amp * np.sin(xx / 97.0) * np.cos(yy / 131.0) + 0.4 * amp * np.sin((xx + yy) / 37.0) + rng.normal(0, sigma, xx.shape)
+    return np.clip(v, 0, 65535).astype(np.uint16)
+
+
+def test_16bit_parallel_pipeline_larger_images(codec):
+    # several tiles per plane and several histogram chunks; every bucket in use; halvings in the popular rows
+    check(codec, gnat16(1500, 1100, 300))                 # contexts spread over hundreds of rows' worth of buckets
+    check(codec, gnat16(1200, 700, 3, amp=200.0))         # 8-bit-like content: few buckets, thousands of halvings per row
+    rng = np.random.default_rng(31)
+    check(codec, rng.integers(0, 65536, (500, 600), dtype=np.uint16))       # contexts up to 65535: rows 0..127 of every bucket
+    rgb = np.stack([gnat16(700, 500, 120, seed=s) for s in (3, 4, 5)], axis=-1)
+    check(codec, np.ascontiguousarray(rgb))
+    check(codec, rng.integers(0, 65536, (300, 257, 3), dtype=np.uint16))    # Co/Cg contexts up to 131070: rows up to 255
+    # width 1 and 2: first-column / first-row neighbour rules only
+    check(codec, gnat16(2, 9000, 50))
+    check(codec, gnat16(9000, 1, 50))
+
+
+def test_16bit_batch_parallel(codec):
+    imgs = np.stack([gnat16(333, 129, 20 * (s + 1), seed=s) for s in range(9)])
+    arena, offsets = codec.compress_batch(imgs)
+    for i, img in enumerate(imgs):
+        assert arena[int(offsets[i]):int(offsets[i + 1])].tobytes() == fo.compress(img), f"image {i}"
+    hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Sixteen, 333, 129)
+    out, status = codec.decompress_batch(arena, offsets, hdr)
+    assert not status.any() and np.array_equal(out, imgs)
+    rgb = np.stack([np.stack([imgs[i], imgs[(i + 1) % 9], imgs[(i + 2) % 9]], axis=-1) for i in range(4)])
+    arena, offsets = codec.compress_batch(rgb)
+    for i, img in enumerate(rgb):
+        assert arena[int(offsets[i]):int(offsets[i + 1])].tobytes() == fo.compress(img), f"rgb image {i}"
+
+
+def test_16bit_random_structured_images(codec):
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 260), st.integers(1, 100), st.booleans(), st.integers(0, 2**31 - 1), st.sampled_from([0, 1, 7, 300, 20000]),
+           st.sampled_from([1, 9, 64]), st.sampled_from(["clip", "wrap", "binary"]))
+    def run(width, height, rgb, seed, noise, period, mode):
+        rng = np.random.default_rng(seed)
+        shape = (height, width, 3) if rgb else (height, width)
+        yy, xx = np.mgrid[0:height, 0:width]
+        base = 32768 + 25000 * np.sin(xx / period) * np.cos(yy / (period + 2.5))
+        if rgb:
+            base = np.stack([base, np.roll(base, 2, 1) * 0.7 + 3000, 65535 - base], axis=-1)
+        v = base + (rng.integers(-noise, noise + 1, shape) if noise else 0)
+        if mode == "clip":
+            img = np.clip(v, 0, 65535)
+        elif mode == "wrap":
+            img = np.mod(v * 3, 65536)
+        else:
+            img = (v > 32768) * 65535
+        check(codec, np.ascontiguousarray(img.astype(np.uint16)))
+
+    run()
+
+
 def test_16bit_truncated(codec):
     img = np.random.default_rng(1).integers(0, 65536, (20, 30), dtype=np.uint16)
     fel = codec.compress(img)
