@@ -49,6 +49,22 @@ def gnat_image(width, height, sigma=3.0, seed=2, phase=0):
     return out
 
 
+W16, H16 = 4096, 4096
+
+
+def gnat16_image(width, height, seed=2):
+    """G-nat scaled to 16 bits (the 16-bit path): amplitudes x 256, noise sigma 192."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((height, width), np.uint16)
+    x = np.arange(width, dtype=np.float64)[None, :]
+    band = 512
+    for y0 in range(0, height, band):
+        y = np.arange(y0, min(height, y0 + band), dtype=np.float64)[:, None]
+        v = 256 * (128 + 60 * np.sin(x / 97) * np.cos(y / 131) + 40 * np.sin((x + y) / 37)) + rng.normal(0, 192, (len(y), width))
+        out[y0:y0 + len(y)] = np.clip(np.rint(v), 0, 65535).astype(np.uint16)
+    return out
+
+
 def tile_batch(n, first=0, seed=1):
     """SURVEY.md 8(d) config 4 integer generator (numpy twin): tile t, pixel (x, y)."""
     t = (np.arange(first, first + n, dtype=np.uint64))[:, None, None]
@@ -163,6 +179,11 @@ def run_reference(args):
         imgs = [tile_batch(per, first=r * args.tiles) for r in range(n)]
         sample = f"{per} of {args.tiles} 512x512 tiles per replica, {n} replica(s), one image per thread"
         px_per_step = per * TILE_W * TILE_H * n
+    elif args.workload == "gray16":
+        rows = 2048
+        imgs = [gnat16_image(W16, rows, seed=2 + r) for r in range(n)]
+        sample = f"top {rows} rows (4096x{rows}) of each replica's 4096x4096 gray16 image, {n} replica(s), one image per thread"
+        px_per_step = W16 * rows * n
     elif args.workload == "rgb":
         rows = 1024  # bounded sample: the top 1024 rows of each replica's frame (7.9 MPixel, 23.6 MSample)
         imgs = [gnat_rgb(W3, rows, rank=r) for r in range(n)]
@@ -199,7 +220,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
         "config": {"workload": workload_name(args), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "MPixel/s", "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference's Rust loops (no Rust toolchain in the image); a single image is serial in the reference"},
@@ -219,6 +240,8 @@ W3, H3 = 7680, 4320
 def workload_name(args):
     if args.workload == "rgb":
         return "configs[2]: one synthetic 7680x4320 8-bit RGB frame (three G-nat planes, YCoCg-R inside the timed path) per GPU, encode"
+    if args.workload == "gray16":
+        return "SURVEY 8(f)1: one synthetic 4096x4096 gray16 image (G-nat x 256, noise sigma 192, seed 2+rank) per GPU, encode"
     if args.workload == "tiles":
         return f"configs[3]-style: {args.tiles} synthetic 512x512 gray8 tiles per GPU (integer generator, seed 1), encode"
     return "configs[1]: one synthetic 8192x8192 gray8 image (G-nat, seed 2+rank) per GPU, encode"
@@ -248,6 +271,10 @@ def run_ours(args):
         chunk = 256
         host = np.concatenate([tile_batch(min(chunk, n_img - s), first=rank * n_img + s) for s in range(0, n_img, chunk)])
         hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, TILE_W, TILE_H)
+    elif args.workload == "gray16":
+        n_img = 1
+        host = gnat16_image(W16, H16, seed=2 + rank)[None]
+        hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Sixteen, W16, H16)
     elif args.workload == "rgb":
         n_img = 1
         host = gnat_rgb(W3, H3, rank=rank)[None]
@@ -256,11 +283,12 @@ def run_ours(args):
         n_img = 1
         host = gnat_image(W2, H2, seed=2 + rank)[None]
         hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, W2, H2)
-    samples = int(host.size)                                   # bytes in = samples (u8)
+    samples = int(host.size)
+    in_bytes = int(host.nbytes)                                # S * b of SURVEY.md 8(d)
     pixels = samples // (3 if args.workload == "rgb" else 1)   # an RGB pixel is one pixel, three samples
-    pin_in = torch.from_numpy(host).pin_memory()
+    pin_in = torch.from_numpy(host.view(np.uint8)).pin_memory()
     d_in = pin_in.to(dev, non_blocking=True)
-    cap = samples + samples // 2 + 4096 * n_img
+    cap = in_bytes + in_bytes // 2 + 4096 * n_img
     d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
     pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -328,7 +356,7 @@ def run_ours(args):
     clocks = sampler.stop()
 
     # decode (reported, not the target): the same .fel decoded on the GPU, timed once per step budget
-    d_pix_out = torch.empty(samples, dtype=torch.uint8, device=dev)
+    d_pix_out = torch.empty(in_bytes, dtype=torch.uint8, device=dev)
     dec_steps = 1 if args.workload != "tiles" else min(args.steps, 3)
     codec.profile(True)
     t0 = time.perf_counter()
@@ -381,7 +409,7 @@ def run_ours(args):
         enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane")}
         dom = max(enc_stages, key=lambda k: enc_stages[k][0])
         dom_ms, dom_launches = enc_stages[dom]
-        alg_bytes = samples + fel_bytes         # S*b + C, per launch: one launch covers the whole batch
+        alg_bytes = in_bytes + fel_bytes        # S*b + C, per launch: one launch covers the whole batch
         dom_avg_ms = dom_ms / max(dom_launches, 1)
         launches_per_step = max(dom_launches / max(args.steps, 1), 1.0)   # batches larger than the scratch budget run in several sub-batches
         alg_bytes_per_launch = alg_bytes / launches_per_step
@@ -399,6 +427,15 @@ def run_ours(args):
             sample = "first 64 tiles of rank 0's batch, 1 thread"
             want = fo.compress(host[0])
             got = d_out[: int(offsets[1])].cpu().numpy().tobytes()
+        elif args.workload == "gray16":
+            rows = 2048
+            t0 = time.perf_counter()
+            fo.compress(host[0][:rows])
+            cpu_s = time.perf_counter() - t0
+            cpu_px = W16 * rows
+            sample = f"top {rows} rows of rank 0's image (4096x{rows} gray16), 1 thread (a single image is serial in the reference)"
+            want = None
+            got = d_out[:fel_bytes].cpu().numpy().tobytes()
         elif args.workload == "rgb":
             rows = 1024
             t0 = time.perf_counter()
@@ -428,7 +465,7 @@ def run_ours(args):
         line = {
             "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
+            "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
             "config": {"workload": workload_name(args), "l2": "flushed between timed steps (256 MiB device write); each step timed with CUDA events on the launching stream",
                        "fel_bytes_rank0": fel_bytes, "bits_per_sample": 8.0 * fel_bytes / samples,
                        "msample_per_s": value * samples / pixels},
@@ -437,7 +474,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "kernel_ms_per_launch": dom_avg_ms, "kernel_launches_per_step": launches_per_step,
                          "whole_encode_achieved_gbs": whole_achieved, "whole_encode_frac": whole_achieved / peak},
             "cpu_baseline": {"value": cpu_px / cpu_s / 1e6, "unit": "MPixel/s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": samples, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
+            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
                     "ms_per_step": tot_e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -459,7 +496,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["image", "rgb", "tiles"], default="image")
+    ap.add_argument("--workload", choices=["image", "rgb", "tiles", "gray16"], default="image")
     ap.add_argument("--tiles", type=int, default=2048, help="tiles per GPU for --workload tiles")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check of the timed output")
     ap.add_argument("--no-decode", dest="decode", action="store_false", help="skip the (slow, single-stream) decode measurement")
