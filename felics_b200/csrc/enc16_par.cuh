@@ -17,7 +17,7 @@ constexpr uint32_t E16_BITS = 17;         // residuals of Co/Cg planes reach 131
 
 // Stable grouping by bucket: k_scatter's scheme (warp w owns 512 consecutive pixels, 32 at a time, ranks by match_any),
 // with {residual | row << 17, pixel index} records.
-__global__ void __launch_bounds__(TILE_THREADS, 2) k16_scatter(const int32_t *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp,
+__global__ void __launch_bounds__(TILE_THREADS, 3) k16_scatter(const int32_t *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp,
                                                                uint32_t cap, const uint32_t *__restrict__ tile_base, uint2 *__restrict__ grp) {
     __shared__ uint16_t wcnt[TILE_WARPS][NBIN];
     __shared__ uint32_t wbase[TILE_WARPS][NBIN];
@@ -107,36 +107,39 @@ __device__ __forceinline__ void scan_costs16(uint32_t (&P)[NK16], uint32_t lane,
     for (int k = N; k < NK16; k++) P[k] = (1u + (uint32_t)k) * cnt;
 }
 
-// Fast pass of the bucket walk: 128 consecutive elements of ONE row whose residuals are all below 2^N (N = 4 or 8), four
-// consecutive elements per lane.  Costs of k < N are prefix-summed (inside the lane, then over the lanes); for k >= N the
-// cost is 1 + k per element, so the prefix is a multiple of the element index.  Within an epoch the counters only grow:
-// the halving element is in the first lane whose LAST element has all counters past 1024.
+// Wide pass of the bucket walk: 128 consecutive elements of the bucket, four consecutive elements per lane, of which the
+// ones flagged `in` belong to the row being walked (the others cost nothing and are never a halving or a get_k).  The costs
+// of k < N are prefix-summed inside the lane and then over the lanes (N: every residual of the row is below 2^N, or 15);
+// for k >= N the cost is 1 + k per element of the row, so the prefix is a multiple of the running element count.
+// All sums travel times 16 with 14 - k in the low bits: a counter x is the key x * 16 + (14 - k), whose minimum over k is
+// get_k's answer (smallest count, ties to the largest k: parameter_selection.rs:78-83) and, shifted back, the smallest
+// count itself (the halving test of parameter_selection.rs:58).  Within an epoch the counters only grow: the halving
+// element is in the first lane whose LAST element has all counters past 1024.
 template <int N>
-__device__ __forceinline__ void bw16_fast128(const uint4 ra, const uint4 rb, uint32_t lane, uint32_t *__restrict__ trow /* estimator row, shared */,
-                                             uint32_t *__restrict__ sx /* 16 words, shared */, uint8_t *__restrict__ kp) {
-    const uint32_t emask = (1u << E16_BITS) - 1u;
-    const uint32_t e[4] = {ra.x & emask, ra.z & emask, rb.x & emask, rb.z & emask};
-    const uint32_t pix[4] = {ra.y, ra.w, rb.y, rb.w};
-    // All sums are kept times 16: a counter x travels as the key x * 16 + (14 - k), whose minimum over k is get_k's answer
-    // (smallest count, ties to the largest k: parameter_selection.rs:78-83) and, shifted back, the smallest count itself.
-    uint32_t q[4][N], o[N];
+__device__ __forceinline__ void bw16_pass128(const uint32_t (&e)[4], const bool (&in)[4], const uint32_t (&pix)[4], uint32_t lane,
+                                             uint32_t *__restrict__ trow /* estimator row, shared */, uint32_t *__restrict__ sx /* 16 words, shared */,
+                                             uint8_t *__restrict__ kp) {
+    constexpr int NS = N < NK16 ? N + 1 : N;    // scanned quantities: the costs and, when a tail exists, the element count
+    uint32_t q[4][NS], o[NS];
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-        q[0][k] = ((e[0] >> k) + 1u + (uint32_t)k) << 4;
+    for (int k = 0; k < NS; k++) {
 #pragma unroll
-        for (int i = 1; i < 4; i++) q[i][k] = q[i - 1][k] + (((e[i] >> k) + 1u + (uint32_t)k) << 4);
+        for (int i = 0; i < 4; i++) {
+            const uint32_t c = k < N ? (((e[i] >> k) + 1u + (uint32_t)k) << 4) : 16u;
+            q[i][k] = (i ? q[i ? i - 1 : 0][k] : 0u) + (in[i] ? c : 0u);
+        }
         o[k] = q[3][k];
     }
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-        for (int k = 0; k < N; k++) {
+        for (int k = 0; k < NS; k++) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, o[k], d);
             if (lane >= (uint32_t)d) o[k] += t;
         }
     }
 #pragma unroll
-    for (int k = 0; k < N; k++) o[k] -= q[3][k];   // exclusive over lanes
+    for (int k = 0; k < NS; k++) o[k] -= q[3][k];   // exclusive over lanes
     uint32_t V[NK16], Vo[NK16];
     {
         const uint4 *t4 = reinterpret_cast<const uint4 *>(trow);
@@ -144,43 +147,37 @@ __device__ __forceinline__ void bw16_fast128(const uint4 ra, const uint4 rb, uin
         V[0] = a.x; V[1] = a.y; V[2] = a.z; V[3] = a.w; V[4] = b.x; V[5] = b.y; V[6] = b.z; V[7] = b.w;
         V[8] = c.x; V[9] = c.y; V[10] = c.z; V[11] = c.w; V[12] = d.x; V[13] = d.y; V[14] = d.z;
     }
-    // key of counter k before my element i: Vo[k] + (k < N ? q[i-1][k] : 16 * (1 + k) * i); after it: Vo[k] + (k < N ? q[i][k] : 16 * (1 + k) * (i + 1))
+    // key of counter k after my element i: Vo[k] + (k < N ? q[i][k] : (1 + k) * q[i][N]); before it: the same with i - 1 (nothing for i = 0)
     auto rebase = [&]() {
 #pragma unroll
-        for (int k = 0; k < NK16; k++) Vo[k] = V[k] * 16u + (14u - (uint32_t)k) + (k < N ? o[k < N ? k : 0] : 64u * (1u + (uint32_t)k) * lane);
+        for (int k = 0; k < NK16; k++) Vo[k] = V[k] * 16u + (14u - (uint32_t)k) + (k < N ? o[k < N ? k : 0] : (1u + (uint32_t)k) * o[NS - 1]);
     };
-    auto after_min = [&](int i) {   // smallest counter after element i
+    auto key_min = [&](int i) {   // smallest key after element i (i = -1: before my first element)
         uint32_t m = 0xffffffffu;
 #pragma unroll
-        for (int k = 0; k < NK16; k++) m = min(m, Vo[k] + (k < N ? q[i][k < N ? k : 0] : 16u * (1u + (uint32_t)k) * (uint32_t)(i + 1)));
-        return m >> 4;
-    };
-    auto pick = [&](int i) {        // get_k on the counters before element i
-        uint32_t m = 0xffffffffu;
-#pragma unroll
-        for (int k = 0; k < NK16; k++) m = min(m, Vo[k] + (k < N ? (i ? q[i ? i - 1 : 0][k < N ? k : 0] : 0u) : 16u * (1u + (uint32_t)k) * (uint32_t)i));
-        return 14u - (m & 15u);
+        for (int k = 0; k < NK16; k++) m = min(m, Vo[k] + (i < 0 ? 0u : (k < N ? q[i < 0 ? 0 : i][k < N ? k : 0] : (1u + (uint32_t)k) * q[i < 0 ? 0 : i][NS - 1])));
+        return m;
     };
     rebase();
     uint32_t myk[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) myk[i] = pick(i);
+    for (int i = 0; i < 4; i++) myk[i] = 14u - (key_min(i - 1) & 15u);
     int done = -1;   // my elements up to `done` lie at or before the last halving
     for (;;) {
-        const uint32_t hit = __ballot_sync(0xffffffffu, done < 3 && after_min(3) > HALVE_AT);
+        const uint32_t hit = __ballot_sync(0xffffffffu, done < 3 && (key_min(3) >> 4) > HALVE_AT);
         if (!hit) break;
         const uint32_t L = (uint32_t)__ffs(hit) - 1u;
         int ih = 3;
 #pragma unroll
-        for (int i = 2; i >= 0; i--)
-            if (i > done && after_min(i) > HALVE_AT) ih = i;
+        for (int i = 3; i >= 0; i--)
+            if (i > done && in[i] && (key_min(i) >> 4) > HALVE_AT) ih = i;
         if (lane == L) {
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 if (i == ih) {
 #pragma unroll
                     for (int k = 0; k < NK16; k++)
-                        sx[k] = k < N ? (o[k < N ? k : 0] + q[i][k < N ? k : 0]) >> 4 : (1u + (uint32_t)k) * (4u * lane + (uint32_t)i + 1u);
+                        sx[k] = k < N ? (o[k < N ? k : 0] + q[i][k < N ? k : 0]) >> 4 : (1u + (uint32_t)k) * ((o[NS - 1] + q[i][NS - 1]) >> 4);
                 }
             sx[15] = (uint32_t)ih;
         }
@@ -198,19 +195,20 @@ __device__ __forceinline__ void bw16_fast128(const uint4 ra, const uint4 rb, uin
         done = lane < L ? 3 : (lane == L ? ih : done);
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (i > done) myk[i] = pick(i);
+            if (i > done) myk[i] = 14u - (key_min(i - 1) & 15u);
     }
     if (lane == 31) {
         uint32_t A[NK16];
 #pragma unroll
-        for (int k = 0; k < NK16; k++) A[k] = (Vo[k] + (k < N ? q[3][k < N ? k : 0] : 64u * (1u + (uint32_t)k))) >> 4;
+        for (int k = 0; k < NK16; k++) A[k] = (Vo[k] + (k < N ? q[3][k < N ? k : 0] : (1u + (uint32_t)k) * q[3][NS - 1])) >> 4;
         uint4 *t4 = reinterpret_cast<uint4 *>(trow);
         t4[0] = make_uint4(A[0], A[1], A[2], A[3]); t4[1] = make_uint4(A[4], A[5], A[6], A[7]);
         t4[2] = make_uint4(A[8], A[9], A[10], A[11]); t4[3] = make_uint4(A[12], A[13], A[14], 0u);
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; i++) kp[pix[i]] = (uint8_t)myk[i];
+    for (int i = 0; i < 4; i++)
+        if (in[i]) kp[pix[i]] = (uint8_t)myk[i];
 }
 
 // Rows are independent, so four warps share a bucket: warp `way` takes the rows with (row & 3) == way.
@@ -244,24 +242,28 @@ __global__ void __launch_bounds__(32 * BW_WAYS) k16_bwalk(const uint2 *__restric
         uint32_t pf = 0xffffffffu;
         for (uint32_t first = 0; first < count; first += 32) {
             if ((first & 127u) == 0 && first + 128 <= count && (opts & 8u) == 0) {
-                // 128 elements of one row with small residuals: the fast pass
+                // 128 elements whose rows are all below 8 (contexts below 4096): at most two rows are mine, one wide pass each
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(src + first) + 2 * lane;
                 uint4 ra = pa, rb = pb;
                 if (pf != first) { ra = s4[0]; rb = s4[1]; }
                 if (first + 256 <= count) { pa = s4[64]; pb = s4[65]; pf = first + 128; }
-                const uint32_t r0 = __shfl_sync(0xffffffffu, ra.x, 0) >> E16_BITS;
-                const bool one_row = __all_sync(0xffffffffu, (ra.x >> E16_BITS) == r0 && (ra.z >> E16_BITS) == r0 && (rb.x >> E16_BITS) == r0 && (rb.z >> E16_BITS) == r0);
-                if (one_row) {
-                    const uint32_t emask = (1u << E16_BITS) - 1u;
-                    const uint32_t bits = __reduce_or_sync(0xffffffffu, (ra.x | ra.z | rb.x | rb.z) & emask);
-                    if (bits < 256u) {
-                        if ((r0 & waymask) == way) {
-                            if (bits < 16u) bw16_fast128<4>(ra, rb, lane, tab[r0], sP[0], kp);
-                            else bw16_fast128<8>(ra, rb, lane, tab[r0], sP[0], kp);
-                        }
-                        first += 96;
-                        continue;
+                const uint32_t emask = (1u << E16_BITS) - 1u;
+                const uint32_t rows[4] = {ra.x >> E16_BITS, ra.z >> E16_BITS, rb.x >> E16_BITS, rb.z >> E16_BITS};
+                if (__reduce_or_sync(0xffffffffu, rows[0] | rows[1] | rows[2] | rows[3]) < 8u && waymask == 3u) {
+                    const uint32_t e[4] = {ra.x & emask, ra.z & emask, rb.x & emask, rb.z & emask};
+                    const uint32_t pix[4] = {ra.y, ra.w, rb.y, rb.w};
+#pragma unroll 1
+                    for (uint32_t prow = way; prow < 8u; prow += 4u) {
+                        const bool in[4] = {rows[0] == prow, rows[1] == prow, rows[2] == prow, rows[3] == prow};
+                        const uint32_t mybits = (in[0] ? e[0] : 0u) | (in[1] ? e[1] : 0u) | (in[2] ? e[2] : 0u) | (in[3] ? e[3] : 0u);
+                        if (!__any_sync(0xffffffffu, in[0] || in[1] || in[2] || in[3])) continue;
+                        const uint32_t bits = __reduce_or_sync(0xffffffffu, mybits);
+                        if (bits < 16u) bw16_pass128<4>(e, in, pix, lane, tab[prow], sP[0], kp);
+                        else if (bits < 256u) bw16_pass128<8>(e, in, pix, lane, tab[prow], sP[0], kp);
+                        else bw16_pass128<NK16>(e, in, pix, lane, tab[prow], sP[0], kp);
                     }
+                    first += 96;
+                    continue;
                 }
             }
             const uint32_t nv = min(32u, count - first);
