@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
     L.felics_compress_batch_device.argtypes = [vp, sz, vp, hp, vp, sz, u64p]
     L.felics_decompress_batch.argtypes = [vp, sz, vp, u64p, hp, vp, C.POINTER(C.c_int)]
     L.felics_decompress_batch_device.argtypes = [vp, sz, vp, u64p, hp, vp, C.POINTER(C.c_int)]
+    L.felics_sidecar_build.argtypes = [vp, C.c_uint32, vp, sz, C.POINTER(sz)]
+    L.felics_decompress_sidecar.argtypes = [vp, vp, sz, vp, sz, vp, sz, hp]
     L.felics_profile_enable.argtypes = [vp, C.c_int]
     L.felics_profile_reset.argtypes = [vp]
     L.felics_profile_stage_name.argtypes = [C.c_int]
@@ -243,6 +245,33 @@ class Codec:
         src = np.frombuffer(fel, dtype=np.uint8)
         ch = _CHeader()
         rc = self._lib.felics_decompress(self._h, src.ctypes.data, len(src), out.ctypes.data, max(out.nbytes, 1), C.byref(ch))
+        if rc:
+            _raise(rc)
+        return out
+
+    # ---- band sidecar: opt-in, NOT part of the reference format (include/felics_b200.h) ----------
+    def compress_with_sidecar(self, image: np.ndarray, band_rows: int = 0):
+        """(fel, sidecar): the reference-format bytes of `compress` plus a side file that lets the bands of the image
+        decode in parallel (`decompress_with_sidecar`).  8-bit images of more than two pixels only."""
+        fel = self.compress(image)
+        n = C.c_size_t(0)
+        rc = self._lib.felics_sidecar_build(self._h, band_rows, None, 0, C.byref(n))
+        if rc != -8:
+            _raise(rc if rc else -12)
+        out = np.empty(n.value, dtype=np.uint8)
+        rc = self._lib.felics_sidecar_build(self._h, band_rows, out.ctypes.data, out.size, C.byref(n))
+        if rc:
+            _raise(rc)
+        return fel, out.tobytes()
+
+    def decompress_with_sidecar(self, fel: bytes, sidecar: bytes) -> np.ndarray:
+        hdr = read_header(fel)
+        out = np.zeros(_shape_of(hdr), dtype=_dtype_of(hdr))
+        src = np.frombuffer(fel, dtype=np.uint8)
+        side = np.frombuffer(sidecar, dtype=np.uint8)
+        ch = _CHeader()
+        rc = self._lib.felics_decompress_sidecar(self._h, src.ctypes.data, len(src), side.ctypes.data, len(side), out.ctypes.data,
+                                                 max(out.nbytes, 1), C.byref(ch))
         if rc:
             _raise(rc)
         return out

@@ -297,6 +297,21 @@ int felics_decompress(felics_ctx *ctx, const uint8_t *fel, size_t len, void *pix
     return felics_decompress_batch(ctx, 1, fel, off, &hdr, pixels_out, &status);
 }
 
+int felics_sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *sidecar_out, size_t cap, size_t *out_len) {
+    if (!ctx || (!sidecar_out && cap)) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    return sidecar_build(ctx, band_rows, sidecar_out, cap, out_len);
+}
+
+int felics_decompress_sidecar(felics_ctx *ctx, const uint8_t *fel, size_t len, const uint8_t *sidecar, size_t sidecar_len, void *pixels_out,
+                              size_t cap, felics_header *hdr_out) {
+    if (!ctx || !fel || !sidecar || (!pixels_out && cap)) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    return decode_sidecar(ctx, fel, len, sidecar, sidecar_len, pixels_out, cap, hdr_out);
+}
+
 int felics_decompress_device(felics_ctx *ctx, const uint8_t *d_fel, size_t len, void *d_pixels_out, size_t cap, felics_header *hdr_out) {
     if (!ctx || !d_fel) return FELICS_ERR_INVALID_ARGUMENT;
     int rc = bind_device(ctx);

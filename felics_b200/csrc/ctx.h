@@ -32,6 +32,19 @@ enum Stage : int {
 
 struct ProfEntry { int stage; cudaEvent_t a, b; };
 
+// What the sidecar builder (sidecar.cuh) needs from the last single-image 8-bit encode: pointers into the context's scratch
+// (valid until the next call on the context) and the geometry they belong to.
+struct LastEncode {
+    bool valid = false;
+    uint32_t w = 0, h = 0, npix = 0, nch = 0, tpp = 0, cap = 0;
+    const void *planes = nullptr;    // u8 samples (gray) or i16 planes (RGB)
+    bool planes_u8 = false;
+    const uint32_t *tile_base = nullptr, *chain_count = nullptr, *chain_base = nullptr, *blk_rec = nullptr, *blk_epoch = nullptr, *ep_rec = nullptr;
+    const uint16_t *e_grp = nullptr;
+    const uint64_t *tile_off = nullptr, *plane_bits = nullptr;
+    uint64_t fel_bytes = 0;
+};
+
 void set_error(const char *fmt, ...);
 
 }  // namespace felics
@@ -65,7 +78,7 @@ struct felics_ctx {
     void *tables16 = nullptr;
     size_t tables16_cap = 0;
     uint32_t tag16 = 1;
-    size_t decode_smem_set = 0, dec16_smem_set = 0;
+    size_t decode_smem_set = 0, dec16_smem_set = 0, decode_bands_smem_set = 0;
 
     bool prof = false;
     bool no_overlap = false;      // debug/profiling switch: run the serial walk after the speculative one, on the same stream
@@ -83,6 +96,7 @@ struct felics_ctx {
     const uint32_t *dbg_rec = nullptr;
     size_t dbg_rec_count = 0;
     uint32_t dbg_counters[8] = {0};
+    felics::LastEncode last;          // for felics_sidecar_build
 };
 
 namespace felics {
@@ -121,6 +135,10 @@ int encode16_serial_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels
                                  uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);
 int tables16(felics_ctx *ctx, size_t images, uint32_t **out);
 uint32_t next_tags16(felics_ctx *ctx);
+// sidecar (opt-in, NOT the reference format): band snapshots that let one big image decode in parallel
+int sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *h_out, size_t cap, size_t *out_len);
+int decode_sidecar(felics_ctx *ctx, const uint8_t *h_fel, size_t len, const uint8_t *h_side, size_t side_len, void *h_pixels_out, size_t cap,
+                   felics_header *hdr_out);
 // decode.cu
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host);

@@ -9,8 +9,10 @@
 #include "ctx.h"
 #include "device_common.cuh"
 #include "serial16.cuh"
+#include "sidecar.cuh"
 
 #include <algorithm>
+#include <cstring>
 
 namespace felics {
 
@@ -236,6 +238,105 @@ struct BitWindow {
     __device__ __forceinline__ bool eof() const { return used > limit; }
 };
 
+// Rows [y0, y1) of one plane, decoded by lane 0 and written out by the warp.  `rows` is the two-row buffer: when y0 > 0 the
+// caller has put row y0 - 1 into its ((y0 & 1) ^ 1) half; col0_a / col0_b are the first samples of rows y0 - 1 and y0 - 2.
+__device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t *rows, int16_t *pl, uint32_t w, uint32_t y0, uint32_t y1,
+                                       int32_t p1, int32_t p2, int col0_a, int col0_b, uint32_t lane, int st) {
+    for (uint32_t y = y0; y < y1 && st == FELICS_OK; y++) {
+        int16_t *cur = rows + (size_t)(y & 1u) * w;
+        const int16_t *up = rows + (size_t)((y & 1u) ^ 1u) * w;
+        if (lane == 0) {
+            // neighbours (misc.rs:6-24) without a per-pixel case split: inside a row v1 is the previous sample and
+            // v2 = upp[x]; `upp` is the row above, or this row shifted by two on the first row (i-1, i-2); the
+            // first sample of a row takes (v1, v2) = (left, b0): up / up-up, or up / up-right on the second row
+            uint32_t x = 0;
+            int left = 0, b0 = 0;
+            const int16_t *upp = up;
+            if (y == 0) {
+                cur[0] = (int16_t)p1; left = p1;
+                x = 1;
+                if (w >= 2) { cur[1] = (int16_t)p2; left = p2; x = 2; }
+                upp = cur - 2;
+            } else if (y == 1) {
+                if (w == 1) { cur[0] = (int16_t)p2; x = 1; }     // 1-wide image: the second raw sample is (0, 1)
+                else { left = up[0]; b0 = up[1]; }
+            } else {
+                left = col0_a; b0 = col0_b;
+            }
+            for (; x < w; x++) {
+                const int v1 = left, v2 = x == 0 ? b0 : upp[x];
+                const int hi = max(v1, v2), lo = min(v1, v2);
+                const uint32_t ctx = (uint32_t)(hi - lo);
+                if (ctx > 510u) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
+                const uint32_t top = br.peek32();
+                int value;
+                if (top >> 31) {                                        // InRange (:208-215)
+                    const uint32_t nn = ctx + 1;
+                    const int m = 31 - __clz(nn);
+                    const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                    // marker + m bits (+ 1): at most 11 bits, all inside the window
+                    uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;
+                    int used = 1 + m;
+                    if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
+                    br.skip(used);
+                    br.refill();
+                    xx += left_p;                                       // rotate_left (:55-57)
+                    if (xx >= nn) xx -= nn;
+                    if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
+                    value = lo + (int)xx;
+                } else {
+                    const uint32_t above = (top >> 30) & 1u;
+                    uint32_t *row = tab + ctx * NK;
+                    const uint2 r01 = *reinterpret_cast<const uint2 *>(row), r23 = *reinterpret_cast<const uint2 *>(row + 2), r45 = *reinterpret_cast<const uint2 *>(row + 4);
+                    uint32_t rr[NK] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y};
+                    const int k = argmin_last(rr);                      // get_k (:202)
+                    br.skip(2);
+                    br.refill();
+                    uint32_t q = 0;                                     // read_unary0
+                    for (;;) {
+                        const uint32_t ones = __clz(~br.peek32());      // 32 when all ones
+                        if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
+                        q += 32; br.skip(32); br.refill();
+                        if (br.eof()) break;
+                    }
+                    const uint32_t rem = br.read(k);
+                    if (br.eof()) { st = FELICS_ERR_IO; break; }
+                    if (q > 70000u) { st = FELICS_ERR_INVALID_VALUE; break; }
+                    const uint32_t e = (q << k) + rem;
+                    uint32_t mn = 0xffffffffu;
+#pragma unroll
+                    for (int kk = 0; kk < NK; kk++) {                   // update (parameter_selection.rs:49-65)
+                        rr[kk] += (e >> kk) + 1u + (uint32_t)kk;
+                        mn = min(mn, rr[kk]);
+                    }
+                    if (mn > HALVE_AT) {
+#pragma unroll
+                        for (int kk = 0; kk < NK; kk++) rr[kk] >>= 1;
+                    }
+                    *reinterpret_cast<uint2 *>(row) = make_uint2(rr[0], rr[1]);
+                    *reinterpret_cast<uint2 *>(row + 2) = make_uint2(rr[2], rr[3]);
+                    *reinterpret_cast<uint2 *>(row + 4) = make_uint2(rr[4], rr[5]);
+                    value = above ? hi + (int)e + 1 : lo - (int)e - 1;  // (:216-243)
+                }
+                if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
+                cur[x] = (int16_t)value;
+                left = value;
+            }
+            if (br.eof()) st = FELICS_ERR_IO;   // the reference fails at the read that runs out of input, before any later check
+            col0_b = col0_a;
+            col0_a = cur[0];
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+        __syncwarp();
+        if (st == FELICS_OK) {
+            int16_t *dst = pl + (size_t)y * w;
+            for (uint32_t x = lane; x < w; x += 32) dst[x] = cur[x];
+        }
+        __syncwarp();
+    }
+    return st;
+}
+
 __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
     extern __shared__ __align__(16) unsigned char dec_smem[];
     uint32_t *tab = reinterpret_cast<uint32_t *>(dec_smem);                         // [(NBIN-1) * NK]
@@ -285,99 +386,7 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
         }
         st = __shfl_sync(0xffffffffu, st, 0);
         if (st != FELICS_OK || a.npix == 0) continue;
-        int col0_a = 0, col0_b = 0;   // samples at x = 0 of the previous row and of the row before it
-        for (uint32_t y = 0; y < h && st == FELICS_OK; y++) {
-            int16_t *cur = rows + (size_t)(y & 1u) * w;
-            const int16_t *up = rows + (size_t)((y & 1u) ^ 1u) * w;
-            if (lane == 0) {
-                // neighbours (misc.rs:6-24) without a per-pixel case split: inside a row v1 is the previous sample and
-                // v2 = upp[x]; `upp` is the row above, or this row shifted by two on the first row (i-1, i-2); the
-                // first sample of a row takes (v1, v2) = (left, b0): up / up-up, or up / up-right on the second row
-                uint32_t x = 0;
-                int left = 0, b0 = 0;
-                const int16_t *upp = up;
-                if (y == 0) {
-                    cur[0] = (int16_t)p1; left = p1;
-                    x = 1;
-                    if (w >= 2) { cur[1] = (int16_t)p2; left = p2; x = 2; }
-                    upp = cur - 2;
-                } else if (y == 1) {
-                    if (w == 1) { cur[0] = (int16_t)p2; x = 1; }     // 1-wide image: the second raw sample is (0, 1)
-                    else { left = up[0]; b0 = up[1]; }
-                } else {
-                    left = col0_a; b0 = col0_b;
-                }
-                for (; x < w; x++) {
-                    const int v1 = left, v2 = x == 0 ? b0 : upp[x];
-                    const int hi = max(v1, v2), lo = min(v1, v2);
-                    const uint32_t ctx = (uint32_t)(hi - lo);
-                    if (ctx > 510u) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
-                    const uint32_t top = br.peek32();
-                    int value;
-                    if (top >> 31) {                                        // InRange (:208-215)
-                        const uint32_t nn = ctx + 1;
-                        const int m = 31 - __clz(nn);
-                        const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
-                        // marker + m bits (+ 1): at most 11 bits, all inside the window
-                        uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;
-                        int used = 1 + m;
-                        if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
-                        br.skip(used);
-                        br.refill();
-                        xx += left_p;                                       // rotate_left (:55-57)
-                        if (xx >= nn) xx -= nn;
-                        if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
-                        value = lo + (int)xx;
-                    } else {
-                        const uint32_t above = (top >> 30) & 1u;
-                        uint32_t *row = tab + ctx * NK;
-                        const uint2 r01 = *reinterpret_cast<const uint2 *>(row), r23 = *reinterpret_cast<const uint2 *>(row + 2), r45 = *reinterpret_cast<const uint2 *>(row + 4);
-                        uint32_t rr[NK] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y};
-                        const int k = argmin_last(rr);                      // get_k (:202)
-                        br.skip(2);
-                        br.refill();
-                        uint32_t q = 0;                                     // read_unary0
-                        for (;;) {
-                            const uint32_t ones = __clz(~br.peek32());      // 32 when all ones
-                            if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
-                            q += 32; br.skip(32); br.refill();
-                            if (br.eof()) break;
-                        }
-                        const uint32_t rem = br.read(k);
-                        if (br.eof()) { st = FELICS_ERR_IO; break; }
-                        if (q > 70000u) { st = FELICS_ERR_INVALID_VALUE; break; }
-                        const uint32_t e = (q << k) + rem;
-                        uint32_t mn = 0xffffffffu;
-#pragma unroll
-                        for (int kk = 0; kk < NK; kk++) {                   // update (parameter_selection.rs:49-65)
-                            rr[kk] += (e >> kk) + 1u + (uint32_t)kk;
-                            mn = min(mn, rr[kk]);
-                        }
-                        if (mn > HALVE_AT) {
-#pragma unroll
-                            for (int kk = 0; kk < NK; kk++) rr[kk] >>= 1;
-                        }
-                        *reinterpret_cast<uint2 *>(row) = make_uint2(rr[0], rr[1]);
-                        *reinterpret_cast<uint2 *>(row + 2) = make_uint2(rr[2], rr[3]);
-                        *reinterpret_cast<uint2 *>(row + 4) = make_uint2(rr[4], rr[5]);
-                        value = above ? hi + (int)e + 1 : lo - (int)e - 1;  // (:216-243)
-                    }
-                    if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
-                    cur[x] = (int16_t)value;
-                    left = value;
-                }
-                if (br.eof()) st = FELICS_ERR_IO;   // the reference fails at the read that runs out of input, before any later check
-                col0_b = col0_a;
-                col0_a = cur[0];
-            }
-            st = __shfl_sync(0xffffffffu, st, 0);
-            __syncwarp();
-            if (st == FELICS_OK) {
-                int16_t *dst = pl + (size_t)y * w;
-                for (uint32_t x = lane; x < w; x += 32) dst[x] = cur[x];
-            }
-            __syncwarp();
-        }
+        st = decode_rows(br, tab, rows, pl, w, 0, h, p1, p2, 0, 0, lane, st);
     }
     if (lane == 0) a.status[img] = st;
 }
@@ -648,8 +657,143 @@ static int decode16_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_are
     return FELICS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Band decode with a sidecar (sidecar.cuh; opt-in, not the reference format): one warp per (plane, band) starts from the
+// recorded bit position, estimator table and row above, and must end exactly where the next band starts.
+// ---------------------------------------------------------------------------------------------
+struct BandArgs {
+    const uint32_t *words;
+    uint64_t nwords, fel_bytes;
+    const uint8_t *entries;
+    size_t entry_bytes;
+    uint32_t band_rows, nbands;
+    int16_t *planes;
+    size_t pstride;
+    int *status;
+    uint32_t w, h, npix, nch;
+};
+
+__global__ void __launch_bounds__(32) k_decode_bands(BandArgs a) {
+    extern __shared__ __align__(16) unsigned char dec_smem[];
+    uint32_t *tab = reinterpret_cast<uint32_t *>(dec_smem);
+    int16_t *rows = reinterpret_cast<int16_t *>(dec_smem + (NBIN - 1) * NK * 4 + 8);
+    const uint32_t lane = threadIdx.x;
+    const uint32_t p = blockIdx.x / a.nbands, j = blockIdx.x - p * a.nbands;
+    const uint32_t y0 = j * a.band_rows, y1 = min(a.h, y0 + a.band_rows);
+    if (y0 >= a.h) return;
+    const uint8_t *ent = a.entries + (size_t)blockIdx.x * a.entry_bytes;
+    const uint64_t bit = *reinterpret_cast<const uint64_t *>(ent);
+    const bool last = blockIdx.x + 1 == gridDim.x;   // entries are in stream order: the bands of plane 0, then of plane 1, ...
+    const uint64_t next_bit = last ? 0 : *reinterpret_cast<const uint64_t *>(ent + a.entry_bytes);
+    int st = FELICS_OK;
+    if (bit < 8ull * FELICS_HEADER_BYTES || bit > 8ull * a.fel_bytes) st = FELICS_ERR_CORRUPT;
+    const uint32_t *stab = reinterpret_cast<const uint32_t *>(ent + 16);
+    for (uint32_t t = lane; t < (NBIN - 1) * NK; t += 32) tab[t] = j ? stab[t] : 0u;
+    int col0_a = 0, col0_b = 0;
+    if (j) {
+        const int16_t *srow = reinterpret_cast<const int16_t *>(ent + 16 + (size_t)SIDECAR_TABLE_WORDS * 4);
+        int16_t *up = rows + (size_t)((y0 & 1u) ^ 1u) * a.w;
+        for (uint32_t x = lane; x < a.w; x += 32) up[x] = srow[x];
+        col0_a = srow[0];
+        col0_b = reinterpret_cast<const int32_t *>(ent)[2];
+    }
+    __syncwarp();
+    BitWindow br;
+    int32_t p1 = 0, p2 = 0;
+    if (lane == 0 && st == FELICS_OK) {
+        br.init(a.words, a.nwords, bit, 8 * a.fel_bytes);
+        if (j == 0) {
+            p1 = (int32_t)br.read(32);   // read_signed(32) twice (compression.rs:161-162)
+            p2 = (int32_t)br.read(32);
+            if (br.eof()) st = FELICS_ERR_IO;
+            else if (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767))) st = FELICS_ERR_INVALID_VALUE;
+        }
+    }
+    st = __shfl_sync(0xffffffffu, st, 0);
+    int16_t *pl = a.planes + (size_t)p * a.pstride;
+    if (st == FELICS_OK) st = decode_rows(br, tab, rows, pl, a.w, y0, y1, p1, p2, col0_a, col0_b, lane, st);
+    if (lane == 0) {
+        if (st == FELICS_OK && !last && bit + br.used != next_bit) st = FELICS_ERR_CORRUPT;   // the sidecar does not belong to this file
+        if (st != FELICS_OK) atomicCAS(a.status, FELICS_OK, st);
+    }
+}
+
+int decode_sidecar(felics_ctx *ctx, const uint8_t *h_fel, size_t len, const uint8_t *h_side, size_t side_len, void *h_pixels_out, size_t cap,
+                   felics_header *hdr_out) {
+    ctx->last.valid = false;
+    felics_header hdr;
+    int rc = felics_read_header(h_fel, len, &hdr);
+    if (rc) return rc;
+    if (hdr_out) *hdr_out = hdr;
+    if (hdr.pixel_depth != 0) { set_error("sidecar decode is built for 8-bit samples"); return FELICS_ERR_UNSUPPORTED; }
+    const uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
+    if (npix64 > 0x7fff0000ull) return FELICS_ERR_INVALID_DIMENSIONS;
+    const uint32_t npix = (uint32_t)npix64, nch = hdr.color_type ? 3 : 1;
+    const size_t need = (size_t)npix * nch;
+    if (need > cap) { set_error("pixel buffer too small: need %zu", need); return FELICS_ERR_BUFFER_TOO_SMALL; }
+    uint32_t sh[8];
+    if (side_len < SIDECAR_HEADER_BYTES) { set_error("sidecar too short"); return FELICS_ERR_CORRUPT; }
+    memcpy(sh, h_side, sizeof(sh));
+    const size_t entry = sidecar_entry_bytes(hdr.width);
+    const uint32_t band_rows = sh[5], nbands = sh[6];
+    if (sh[0] != SIDECAR_MAGIC || sh[1] != 1u || sh[2] != hdr.width || sh[3] != hdr.height || sh[4] != nch || band_rows < 2 ||
+        band_rows % sidecar_row_unit(hdr.width ? hdr.width : 1) != 0 || nbands != std::max<uint32_t>(1, (hdr.height + band_rows - 1) / band_rows) ||
+        sh[7] != (uint32_t)entry || side_len != SIDECAR_HEADER_BYTES + (size_t)nch * nbands * entry) {
+        set_error("sidecar header does not match the file");
+        return FELICS_ERR_CORRUPT;
+    }
+    if (npix < 3 || hdr.width > DEC_MAX_W) {   // nothing to gain: the plain decoder
+        uint64_t off[2] = {0, (uint64_t)len};
+        int status = 0;
+        return felics_decompress_batch(ctx, 1, h_fel, off, &hdr, h_pixels_out, &status);
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t fel_al = align_up(len + 8, 256), ent_bytes = side_len - SIDECAR_HEADER_BYTES;
+    if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, fel_al + ent_bytes + 16))) return rc;
+    if ((rc = ensure_buffer(ctx, &ctx->staging_out, &ctx->staging_out_cap, need + 16))) return rc;
+    const size_t pstride = plane_stride8(npix);
+    const size_t plane_bytes = align_up(((size_t)nch * pstride + 8) * sizeof(int16_t), 256);
+    if ((rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, 256 + plane_bytes))) return rc;
+    uint8_t *d_fel = (uint8_t *)ctx->staging_in, *d_ent = d_fel + fel_al;
+    int *d_status = (int *)ctx->scratch;
+    int16_t *d_planes = (int16_t *)((uint8_t *)ctx->scratch + 256);
+    FELICS_CUDA_TRY(cudaMemcpyAsync(d_fel, h_fel, len, cudaMemcpyHostToDevice, st));
+    FELICS_CUDA_TRY(cudaMemcpyAsync(d_ent, h_side + SIDECAR_HEADER_BYTES, ent_bytes, cudaMemcpyHostToDevice, st));
+    FELICS_CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    BandArgs a;
+    a.words = (const uint32_t *)d_fel; a.nwords = (len + 3) / 4; a.fel_bytes = len;
+    a.entries = d_ent; a.entry_bytes = entry; a.band_rows = band_rows; a.nbands = nbands;
+    a.planes = d_planes; a.pstride = pstride; a.status = d_status; a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch;
+    {
+        StageScope s(ctx, ST_DECODE);
+        const size_t smem = (size_t)(NBIN - 1) * NK * 4 + 8 + 2 * (size_t)hdr.width * sizeof(int16_t);
+        if (smem > 48 * 1024 && smem > ctx->decode_bands_smem_set) {
+            FELICS_CUDA_TRY(cudaFuncSetAttribute(k_decode_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->decode_bands_smem_set = smem;
+        }
+        k_decode_bands<<<nch * nbands, 32, smem, st>>>(a);
+        s.launched();
+    }
+    {
+        StageScope s(ctx, ST_UNPLANE);
+        const size_t total = npix;
+        const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);
+        if (nch == 1) k_unplane_gray8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)ctx->staging_out, npix, pstride, total, d_status);
+        else k_unplane_rgb8<<<blocks, 256, 0, st>>>(d_planes, (uint8_t *)ctx->staging_out, npix, pstride, total, d_status);
+        s.launched();
+    }
+    int status = 0;
+    FELICS_CUDA_TRY(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FELICS_CUDA_TRY(cudaMemcpyAsync(h_pixels_out, ctx->staging_out, need, cudaMemcpyDeviceToHost, st));
+    FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+    FELICS_CUDA_TRY(cudaGetLastError());
+    if ((rc = profile_collect(ctx))) return rc;
+    return status;
+}
+
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host) {
+    ctx->last.valid = false;
     if (((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;

@@ -1180,6 +1180,8 @@ Layout carve(uint8_t *base, const Geom &g, size_t ni) {
 
 }  // namespace felics
 #include "enc16_par.cuh"
+#define FELICS_SIDECAR_BUILDER
+#include "sidecar.cuh"
 namespace felics {
 
 // Exactly one of d_arena (device memory, 4-byte aligned) / h_arena (host memory) is non-null.
@@ -1188,6 +1190,7 @@ namespace felics {
 // copy-out of sub-batch i-1 run on their own streams beside the kernels of sub-batch i.
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena,
                         uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels) {
+    ctx->last.valid = false;
     if (d_arena && ((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;
@@ -1521,6 +1524,16 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             FELICS_CUDA_TRY(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_pack[slot], 0));
             FELICS_CUDA_TRY(cudaMemcpyAsync(h_arena + arena_off, target, sub_total, cudaMemcpyDeviceToHost, ctx->copy_out));
             FELICS_CUDA_TRY(cudaEventRecord(ctx->ev_out[slot], ctx->copy_out));
+        }
+        if (n == 1 && g.npix > 2) {
+            LastEncode &le = ctx->last;
+            le.w = g.w; le.h = g.h; le.npix = g.npix; le.nch = g.nch; le.tpp = g.tpp; le.cap = g.cap;
+            le.planes = gray ? (const void *)px : (const void *)L.planes;
+            le.planes_u8 = gray;
+            le.tile_base = L.tile_hist; le.chain_count = L.chain_count; le.chain_base = L.chain_base; le.blk_rec = L.blk_rec;
+            le.blk_epoch = L.blk_epoch; le.ep_rec = L.ep_rec; le.e_grp = L.e_grp; le.tile_off = L.tile_off; le.plane_bits = L.plane_bits;
+            le.fel_bytes = sub_total;
+            le.valid = true;
         }
         ctx->dbg_rec = L.rec;
         ctx->dbg_rec_count = np * (size_t)g.npix;

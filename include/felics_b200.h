@@ -112,6 +112,17 @@ int felics_decompress_batch(felics_ctx *ctx, size_t n, const uint8_t *arena, con
 int felics_decompress_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets,
                                    const felics_header *hdr, void *d_pixels_out, int *status);
 
+/* ---- band sidecar (opt-in; NOT part of the reference .fel format) ----
+ * A .fel file is one serial bit chain per plane (compression.rs:151-248), so one big image decodes on one warp.
+ * felics_sidecar_build writes, for the 8-bit image compressed by the LAST felics_compress / felics_compress_device call
+ * on this context (call it right after, before the input pixels are released), a side file that records the decoder
+ * state at the start of every band of `band_rows` rows (0 = about 64 bands per plane; otherwise a multiple of
+ * 4096 / gcd(width, 4096)).  felics_decompress_sidecar decodes the bands in parallel; the .fel bytes are unchanged and
+ * still decode with felics_decompress.  A sidecar that does not belong to the file yields FELICS_ERR_CORRUPT. */
+int felics_sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *sidecar_out, size_t cap, size_t *out_len);
+int felics_decompress_sidecar(felics_ctx *ctx, const uint8_t *fel, size_t len, const uint8_t *sidecar, size_t sidecar_len,
+                              void *pixels_out, size_t cap, felics_header *hdr_out);
+
 /* Instrumentation (not part of the reference API): per-stage device times from
  * CUDA events on the context's stream, and the number of kernel launches. */
 int felics_profile_enable(felics_ctx *ctx, int on);

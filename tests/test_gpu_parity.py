@@ -394,3 +394,44 @@ def test_random_structured_images(codec):
         check(codec, np.ascontiguousarray(img.astype(np.uint8)))
 
     run()
+
+
+# ---- band sidecar (opt-in, not the reference format): parallel decode of one big image ----
+def test_sidecar_round_trip(codec):
+    rng = np.random.default_rng(5)
+    cases = [
+        (gnat_image(1024, 700), 0),                                             # automatic band height
+        (gnat_image(1024, 700), 4),                                             # many bands: band_rows = one tile
+        (gnat_image(512, 300), 8),
+        (rng.integers(0, 256, (260, 4096), dtype=np.uint8), 2),                 # noise, one row pair per band
+        (np.stack([gnat_image(768, 400, seed=s) for s in (3, 4, 5)], axis=-1), 16),   # RGB: bands of three planes
+        (gnat_image(333, 200), 0),                                              # odd width: one band per plane only
+        (np.clip(128 + rng.normal(0, 1.2, (2048, 1024)), 0, 255).astype(np.uint8), 32),   # long chains with many halvings before each band
+        (gnat_image(2048, 2048), 64),                                           # speculation, hops and serial walk all feed the snapshots
+    ]
+    for img, rows in cases:
+        img = np.ascontiguousarray(img)
+        fel, side = codec.compress_with_sidecar(img, rows)
+        assert fel == fo.compress(img)                                           # the .fel bytes are the reference format, untouched
+        assert np.array_equal(codec.decompress_with_sidecar(fel, side), img), (img.shape, rows)
+        assert np.array_equal(codec.decompress(fel), img)
+
+
+def test_sidecar_rejects_foreign_or_damaged_side_files(codec):
+    a, b = gnat_image(1024, 256, seed=1), gnat_image(1024, 256, seed=2)
+    fel_a, side_a = codec.compress_with_sidecar(a, 4)
+    fel_b, side_b = codec.compress_with_sidecar(b, 4)
+    failure = (felics_b200.DecompressionError, felics_b200.FelicsError)
+    with pytest.raises(failure):                                                 # bands do not end where the next one starts
+        codec.decompress_with_sidecar(fel_a, side_b)
+    with pytest.raises(failure):
+        codec.decompress_with_sidecar(fel_a, side_a[:-4])
+    bad = bytearray(side_a)
+    bad[0] ^= 1
+    with pytest.raises(failure):
+        codec.decompress_with_sidecar(fel_a, bytes(bad))
+    assert np.array_equal(codec.decompress_with_sidecar(fel_a, side_a), a)      # the context survives the failures
+    with pytest.raises(felics_b200.FelicsError):                                 # band_rows must keep band starts on tile boundaries
+        codec.compress_with_sidecar(gnat_image(333, 200), 3)
+    with pytest.raises(felics_b200.FelicsError):                                 # 16-bit: no sidecar
+        codec.compress_with_sidecar(np.zeros((64, 64), np.uint16))
