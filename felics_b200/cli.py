@@ -39,6 +39,8 @@ def cfelics_main(argv=None) -> int:
     ap.add_argument("-i", "--input", required=True, help="The input file.")
     ap.add_argument("-o", "--output", required=True, help="The output felics file.")
     ap.add_argument("-V", "--version", action="version", version=f"cfelics {VERSION}")
+    ap.add_argument("--sidecar", metavar="FILE", help="(not in the reference tool) also write a band side file that lets dfelics "
+                    "decode the image band-parallel; 8-bit images only. The felics file itself is unchanged.")
     args = ap.parse_args(argv)
     img = _read_image(args.input)
     kinds = {(2, np.dtype(np.uint8)): "8-bit grayscale", (2, np.dtype(np.uint16)): "16-bit grayscale",
@@ -52,8 +54,15 @@ def cfelics_main(argv=None) -> int:
         img = np.ascontiguousarray(img[..., ::-1])   # OpenCV decodes to B, G, R
     try:
         import felics_b200
-        with open(args.output, "wb") as out:
-            felics_b200.compress_image(out, img)
+        if args.sidecar:
+            fel, side = felics_b200._default_codec().compress_with_sidecar(img)
+            with open(args.output, "wb") as out:
+                out.write(fel)
+            with open(args.sidecar, "wb") as out:
+                out.write(side)
+        else:
+            with open(args.output, "wb") as out:
+                felics_b200.compress_image(out, img)
     except Exception as e:   # io::Error in the reference
         print(f"Cannot compress image: {e}")
         return 1
@@ -66,6 +75,7 @@ def dfelics_main(argv=None) -> int:
     ap.add_argument("-o", "--output", required=True,
                     help="The output file. The output format will be determined using the extension of the output file.")
     ap.add_argument("-V", "--version", action="version", version=f"dfelics {VERSION}")
+    ap.add_argument("--sidecar", metavar="FILE", help="(not in the reference tool) the side file written by cfelics --sidecar")
     args = ap.parse_args(argv)
     try:
         f = open(args.input, "rb")
@@ -75,7 +85,14 @@ def dfelics_main(argv=None) -> int:
     import felics_b200
     with f:
         try:
-            img = felics_b200.decompress_image(f)
+            if args.sidecar:
+                with open(args.sidecar, "rb") as sf:
+                    img = felics_b200._default_codec().decompress_with_sidecar(f.read(), sf.read())
+            else:
+                img = felics_b200.decompress_image(f)
+        except OSError as e:
+            print(f"Cannot open side file: {e}")
+            return 1
         except felics_b200.DecompressionError as e:
             print(f"Error while decompressing the image: {e.kind}")
             return 1

@@ -65,3 +65,22 @@ def test_round_trip_through_files(tmp_path, kind):
     (tmp_path / "cut.fel").write_bytes(fel.read_bytes()[:40])
     r = run("dfelics", "-i", str(tmp_path / "cut.fel"), "-o", str(back))
     assert r.returncode == 1 and r.stdout.strip() == "Error while decompressing the image: IoError"
+
+
+@pytest.mark.gpu
+def test_round_trip_with_sidecar(tmp_path):
+    # --sidecar is our own extension (not in the reference tools): the felics file stays byte-identical
+    import cv2
+    from oracle import felics_oracle as fo
+    from conftest import gnat_image
+    img = gnat_image(1024, 300)
+    src, fel, side, back = tmp_path / "in.png", tmp_path / "out.fel", tmp_path / "out.flsc", tmp_path / "back.png"
+    cv2.imwrite(str(src), img)
+    r = run("cfelics", "-i", str(src), "-o", str(fel), "--sidecar", str(side))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert fel.read_bytes() == fo.compress(img) and side.read_bytes()[:4] == b"FLSC"
+    r = run("dfelics", "-i", str(fel), "-o", str(back), "--sidecar", str(side))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert np.array_equal(cv2.imread(str(back), cv2.IMREAD_UNCHANGED), img)
+    r = run("dfelics", "-i", str(fel), "-o", str(back), "--sidecar", str(tmp_path / "nope.flsc"))
+    assert r.returncode == 1 and r.stdout.startswith("Cannot open side file:")
