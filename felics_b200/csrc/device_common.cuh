@@ -69,6 +69,54 @@ struct RasterCursor {
     }
 };
 
+// Four consecutive samples at a 4-sample-aligned index: one 32-bit (u8) or 64-bit (i16) load
+__device__ __forceinline__ void load4(const uint8_t *p, int (&v)[4]) {
+    const uint32_t w = *reinterpret_cast<const uint32_t *>(p);
+    v[0] = (int)(w & 255u); v[1] = (int)((w >> 8) & 255u); v[2] = (int)((w >> 16) & 255u); v[3] = (int)(w >> 24);
+}
+__device__ __forceinline__ void load4(const int16_t *p, int (&v)[4]) {
+    const uint2 w = *reinterpret_cast<const uint2 *>(p);
+    v[0] = (int)(int16_t)(w.x & 0xffffu); v[1] = (int)(int16_t)(w.x >> 16); v[2] = (int)(int16_t)(w.y & 0xffffu); v[3] = (int)(int16_t)(w.y >> 16);
+}
+__device__ __forceinline__ PixelClass classify_from(int p, int v1, int v2) {   // compression.rs:118-145 given the two neighbours
+    const int h = max(v1, v2), l = min(v1, v2);
+    PixelClass r;
+    r.delta = h - l;
+    r.lo = l;
+    const bool below = p < l, above = p > h;
+    r.cls = below ? 2 : (above ? 1 : 0);
+    r.val = below ? l - p - 1 : (above ? p - h - 1 : p - l);
+    return r;
+}
+// Classes of the four samples i .. i+3 of a plane whose width is a multiple of four (i, x multiples of four; the group
+// never straddles a row).  Interior groups (x >= 4, y >= 1: left neighbour and the row above) take three loads for four
+// samples; the first row and the first group of a row go through the per-sample rules of RasterCursor::classify.
+// valid[j] is false for samples 0 and 1 of the plane (sent raw, compression.rs:93-108).
+template <typename T>
+__device__ __forceinline__ void classify4(const T *plane, uint32_t i, uint32_t x, uint32_t y, uint32_t w, PixelClass (&pc)[4], bool (&valid)[4]) {
+    if (x >= 4 && y >= 1) {
+        int cur[4], up[4];
+        load4(plane + i, cur);
+        load4(plane + i - w, up);
+        const int left = plane[i - 1];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            pc[j] = classify_from(cur[j], j ? cur[j ? j - 1 : 0] : left, up[j]);
+            valid[j] = true;
+        }
+    } else {
+        RasterCursor<T> c;
+        c.pp = plane + i; c.i = i; c.x = x; c.y = y; c.w = w;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            valid[j] = c.i >= 2;
+            if (valid[j]) pc[j] = c.classify();
+            else { pc[j].delta = 0; pc[j].cls = 0; pc[j].val = 0; pc[j].lo = 0; }
+            c.i++; c.pp++; c.x++;      // stays inside the row: x + 3 < w
+        }
+    }
+}
+
 // Phased-in code of v in [0, n-1] (phase_in_coding.rs:23-84): returns the code value, sets len.
 // long codeword = (x - right_p)/2 + right_p in m bits followed by (x - right_p)&1  ==  x + right_p in m+1 bits.
 __device__ __forceinline__ uint32_t phase_in_code(uint32_t n, uint32_t v, int &len) {

@@ -83,6 +83,38 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist(const T *__restrict__ pla
     }
 }
 
+// The same for planes whose width is a multiple of four: a thread classifies four consecutive samples from three loads.
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS) k_hist4(const T *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp, uint32_t nchunks,
+                                                        uint32_t *__restrict__ tile_hist, uint32_t *__restrict__ chunk_tot) {
+    __shared__ uint32_t h[NBIN];
+    const uint32_t bid = blockIdx.x;
+    const uint32_t p = bid / tpp, t = bid - p * tpp;
+    for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) h[c] = 0;
+    __syncthreads();
+    const T *pl = planes + (size_t)p * npix;
+    RasterCursor<T> cur;
+    cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+#pragma unroll
+    for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
+        if (cur.i < npix) {
+            PixelClass pc[4];
+            bool valid[4];
+            classify4(pl, cur.i, cur.x, cur.y, w, pc, valid);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (valid[q] && pc[q].cls != 0) atomicAdd(&h[pc[q].delta], 1u);
+        }
+        cur.step(4 * TILE_THREADS);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) {
+        const uint32_t v = h[c];
+        tile_hist[(size_t)bid * NBIN + c] = v;
+        if (v) atomicAdd(&chunk_tot[((size_t)p * nchunks + t / CHUNK_TILES) * NBIN + c], v);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // chainscan: one block (512 threads = one per context) per plane
 // ------------------------------------------------------------------------------------
@@ -774,6 +806,24 @@ __global__ void __launch_bounds__(256, 4) k_kfill(const uint16_t *__restrict__ e
     *reinterpret_cast<uint2 *>(k_grp + g) = out;
 }
 
+// code record of one pixel (device_common.cuh: length << 22 | payload): marker + phased-in code, or marker + Rice code
+// with the k of its grouped element (compression.rs:130-145)
+__device__ __forceinline__ uint32_t code_record(const PixelClass &pc, const uint32_t *__restrict__ gi, const uint8_t *__restrict__ kg, uint32_t i) {
+    if (pc.cls == 0) {
+        int len;
+        const uint32_t code = phase_in_code((uint32_t)pc.delta + 1u, (uint32_t)pc.val, len);
+        return ((uint32_t)(len + 1) << 22) | (1u << len) | code;           // '1' marker then the phased-in code
+    }
+    const uint32_t k = kg[gi[i]];
+    const uint32_t e = (uint32_t)pc.val;
+    const uint32_t q = e >> k, rem = e & ((1u << k) - 1u);
+    const uint32_t above = pc.cls == 1 ? 1u : 0u;
+    const uint32_t len = 2u + q + 1u + k;
+    if (len <= (uint32_t)REC_SHORT_MAX)                                     // '0', above, q ones, '0', k remainder bits
+        return (len << 22) | (above << (q + 1u + k)) | (((1u << q) - 1u) << (k + 1u)) | rem;
+    return (len << 22) | (above << 17) | (k << 14) | (rem << 9) | q;
+}
+
 // ------------------------------------------------------------------------------------
 // code: marker + code word per pixel (compression.rs:130-145), bits per tile
 // ------------------------------------------------------------------------------------
@@ -795,29 +845,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code(const T *__restrict__ pla
         const uint32_t i = cur.i;
         if (i >= npix) break;
         uint32_t r = 0;
-        if (i >= 2) {
-            PixelClass pc = cur.classify();
-            if (pc.cls == 0) {
-                int len;
-                uint32_t code = phase_in_code((uint32_t)pc.delta + 1u, (uint32_t)pc.val, len);
-                // '1' marker then the phased-in code
-                r = ((uint32_t)(len + 1) << 22) | (1u << len) | code;
-            } else {
-                uint32_t g = gidx[(size_t)p * npix + i];
-                uint32_t k = k_grp[(size_t)p * cap + g];
-                uint32_t e = (uint32_t)pc.val;
-                uint32_t q = e >> k, rem = e & ((1u << k) - 1u);
-                uint32_t above = pc.cls == 1 ? 1u : 0u;
-                uint32_t len = 2u + q + 1u + k;
-                if (len <= (uint32_t)REC_SHORT_MAX) {
-                    // '0', above, q ones, '0', k remainder bits
-                    uint32_t code = (above << (q + 1u + k)) | (((1u << q) - 1u) << (k + 1u)) | rem;
-                    r = (len << 22) | code;
-                } else {
-                    r = (len << 22) | (above << 17) | (k << 14) | (rem << 9) | q;
-                }
-            }
-        }
+        if (i >= 2) r = code_record(cur.classify(), gidx + (size_t)p * npix, k_grp + (size_t)p * cap, i);
         rec[(size_t)p * npix + i] = r;
         bits += rec_len(r);
         cur.step(TILE_THREADS);
@@ -831,6 +859,49 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code(const T *__restrict__ pla
 #pragma unroll
         for (int q = 0; q < TILE_WARPS; q++) s += wsum[q];
         tile_bits[bid] = s;
+    }
+}
+
+// The same for planes whose width is a multiple of four: four consecutive pixels per thread, records leave as one 16-byte store.
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS) k_code4(const T *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp, uint32_t cap,
+                                                        const uint32_t *__restrict__ gidx, const uint8_t *__restrict__ k_grp, uint32_t *__restrict__ rec,
+                                                        uint32_t *__restrict__ tile_bits) {
+    __shared__ uint32_t wsum[TILE_WARPS];
+    const uint32_t bid = blockIdx.x;
+    const uint32_t p = bid / tpp, t = bid - p * tpp;
+    const T *pl = planes + (size_t)p * npix;
+    const uint32_t *gi = gidx + (size_t)p * npix;
+    const uint8_t *kg = k_grp + (size_t)p * cap;
+    uint32_t bits = 0;
+    RasterCursor<T> cur;
+    cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+#pragma unroll
+    for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
+        const uint32_t i = cur.i;
+        if (i < npix) {
+            PixelClass pc[4];
+            bool valid[4];
+            classify4(pl, i, cur.x, cur.y, w, pc, valid);
+            uint32_t r[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                r[q] = valid[q] ? code_record(pc[q], gi, kg, i + q) : 0u;
+                bits += rec_len(r[q]);
+            }
+            *reinterpret_cast<uint4 *>(rec + (size_t)p * npix + i) = make_uint4(r[0], r[1], r[2], r[3]);   // npix and i are multiples of four
+        }
+        cur.step(4 * TILE_THREADS);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = bits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < TILE_WARPS; q++) sum += wsum[q];
+        tile_bits[bid] = sum;
     }
 }
 
@@ -1286,6 +1357,8 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
 
         // gray samples are classified straight from the caller's pixels; RGB goes through Y/Co/Cg planes
         const bool gray = g.nch == 1;
+        // width a multiple of four (and 4-byte aligned samples): four consecutive samples per thread in the order-free kernels
+        const bool quads = g.w % 4 == 0 && g.w >= 8 && (!gray || ((uintptr_t)px & 3) == 0) && !ctx->no_quads;
         if (g.npix > 0 && !gray) {
             StageScope s(ctx, ST_PLANES);
             size_t total = ni * (size_t)g.npix;
@@ -1299,7 +1372,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 StageScope s(ctx, ST_HIST);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.chunk_tot, 0, np * g.nchunks * NBIN * sizeof(uint32_t), st));
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.counters, 0, 8 * sizeof(uint32_t), st));
-                if (gray) k_hist<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                if (quads && gray) k_hist4<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                else if (quads) k_hist4<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                else if (gray) k_hist<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
                 else k_hist<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
                 s.launched();
             }
@@ -1452,7 +1527,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             }
             {
                 StageScope s(ctx, ST_CODE);
-                if (gray) k_code<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
+                if (quads && gray) k_code4<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
+                else if (quads) k_code4<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
+                else if (gray) k_code<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
                 else k_code<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.gidx, L.k_grp, L.rec, L.tile_bits);
                 s.launched();
             }
