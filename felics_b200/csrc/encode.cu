@@ -258,6 +258,85 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_scatter(const T *__restrict
     }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_scatter4(const T *__restrict__ planes, uint32_t w, uint32_t npix,
+                                                          uint32_t tpp, uint32_t cap, const uint32_t *__restrict__ tile_base,
+                                                          uint16_t *__restrict__ e_grp, uint32_t *__restrict__ gidx) {
+    __shared__ uint16_t wcnt[TILE_WARPS][NBIN];
+    __shared__ uint32_t wbase[TILE_WARPS][NBIN];
+    __shared__ __align__(16) uint32_t xch[TILE_WARPS][128];
+    uint32_t bid = blockIdx.x;
+    uint32_t p = bid / tpp, t = bid - p * tpp;
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c < TILE_WARPS * NBIN; c += TILE_THREADS) (&wcnt[0][0])[c] = 0;
+    __syncthreads();
+    const T *pl = planes + (size_t)p * npix;
+    uint32_t wstart = t * TILE + wid * WARP_PIX;
+    uint32_t info[WARP_ITERS];  // rank(13) | delta(9) << 13 | oor << 22
+    uint16_t ev[WARP_ITERS];
+    const uint32_t lt = (1u << lane) - 1u;
+    // classification four consecutive samples per lane (classify4), then a transpose through shared memory so that the
+    // ranking below still sees 32 consecutive pixels per round, lane = pixel (ranks follow raster order)
+    RasterCursor<T> cur;
+    cur.init(pl, wstart + 4u * lane, w);
+#pragma unroll
+    for (int sup = 0; sup < WARP_ITERS / 4; sup++) {
+        uint32_t word[4] = {0u, 0u, 0u, 0u};   // delta | val << 9 | out-of-range << 31
+        if (cur.i < npix) {
+            PixelClass pc[4];
+            bool valid[4];
+            classify4(pl, cur.i, cur.x, cur.y, w, pc, valid);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (valid[q] && pc[q].cls != 0) word[q] = (uint32_t)pc[q].delta | ((uint32_t)pc[q].val << 9) | 0x80000000u;
+        }
+        *reinterpret_cast<uint4 *>(&xch[wid][4 * lane]) = make_uint4(word[0], word[1], word[2], word[3]);
+        __syncwarp();
+#pragma unroll
+        for (int sl = 0; sl < 4; sl++) {
+            const int it = sup * 4 + sl;
+            const uint32_t wd = xch[wid][32 * sl + lane];
+            const bool oor = wd >> 31;
+            const uint32_t delta = wd & 511u, val = (wd >> 9) & 1023u;
+            const uint32_t act = __ballot_sync(0xffffffffu, oor);
+            uint32_t rank = 0, grpmask = 0, prev = 0;
+            if (oor) {
+                grpmask = __match_any_sync(act, delta);
+                prev = wcnt[wid][delta];
+                rank = prev + __popc(grpmask & lt);
+            }
+            __syncwarp();
+            if (oor && (grpmask & lt) == 0) wcnt[wid][delta] = (uint16_t)(prev + __popc(grpmask));
+            __syncwarp();
+            info[it] = rank | (delta << 13) | (oor ? (1u << 22) : 0u);
+            ev[it] = (uint16_t)val;
+        }
+        cur.step(128);
+    }
+    __syncthreads();
+    // exclusive prefix over warps, per context, on top of the tile's base
+    for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) {
+        uint32_t run = tile_base[(size_t)bid * NBIN + c];
+#pragma unroll
+        for (int q = 0; q < TILE_WARPS; q++) {
+            wbase[q][c] = run;
+            run += wcnt[q][c];
+        }
+    }
+    __syncthreads();
+    uint16_t *eg = e_grp + (size_t)p * cap;
+    uint32_t *gi = gidx + (size_t)p * npix;
+#pragma unroll
+    for (int it = 0; it < WARP_ITERS; it++) {
+        if (info[it] >> 22) {
+            uint32_t delta = (info[it] >> 13) & 511u;
+            uint32_t g = wbase[wid][delta] + (info[it] & 8191u);
+            eg[g] = ev[it];
+            gi[wstart + it * 32 + lane] = g;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // prefix: one block per group of 1024 grouped elements (32 blocks of 32).
 // fine[g] = {U01, U23, U45, e}: inclusive prefix, within the 32-block, of the code cost
@@ -808,13 +887,18 @@ __global__ void __launch_bounds__(256, 4) k_kfill(const uint16_t *__restrict__ e
 
 // code record of one pixel (device_common.cuh: length << 22 | payload): marker + phased-in code, or marker + Rice code
 // with the k of its grouped element (compression.rs:130-145)
+__device__ __forceinline__ uint32_t code_record_g(const PixelClass &pc, const uint8_t *__restrict__ kg, uint32_t g);
 __device__ __forceinline__ uint32_t code_record(const PixelClass &pc, const uint32_t *__restrict__ gi, const uint8_t *__restrict__ kg, uint32_t i) {
+    return code_record_g(pc, kg, pc.cls == 0 ? 0u : gi[i]);
+}
+// the same with the grouped index already at hand (ignored for in-range pixels)
+__device__ __forceinline__ uint32_t code_record_g(const PixelClass &pc, const uint8_t *__restrict__ kg, uint32_t g) {
     if (pc.cls == 0) {
         int len;
         const uint32_t code = phase_in_code((uint32_t)pc.delta + 1u, (uint32_t)pc.val, len);
         return ((uint32_t)(len + 1) << 22) | (1u << len) | code;           // '1' marker then the phased-in code
     }
-    const uint32_t k = kg[gi[i]];
+    const uint32_t k = kg[g];
     const uint32_t e = (uint32_t)pc.val;
     const uint32_t q = e >> k, rem = e & ((1u << k) - 1u);
     const uint32_t above = pc.cls == 1 ? 1u : 0u;
@@ -883,10 +967,12 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code4(const T *__restrict__ pl
             PixelClass pc[4];
             bool valid[4];
             classify4(pl, i, cur.x, cur.y, w, pc, valid);
+            const uint4 g4 = *reinterpret_cast<const uint4 *>(gi + i);   // grouped indices of the quad (stale for in-range pixels: unused)
+            const uint32_t gq[4] = {g4.x, g4.y, g4.z, g4.w};
             uint32_t r[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                r[q] = valid[q] ? code_record(pc[q], gi, kg, i + q) : 0u;
+                r[q] = valid[q] ? code_record_g(pc[q], kg, gq[q]) : 0u;
                 bits += rec_len(r[q]);
             }
             *reinterpret_cast<uint4 *>(rec + (size_t)p * npix + i) = make_uint4(r[0], r[1], r[2], r[3]);   // npix and i are multiples of four
@@ -1391,7 +1477,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
             {
                 StageScope s(ctx, ST_SCATTER);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.e_grp, 0xFF, np * (size_t)g.cap * sizeof(uint16_t), st));
-                if (gray) k_scatter<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
+                if (quads && gray) k_scatter4<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
+                else if (quads) k_scatter4<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
+                else if (gray) k_scatter<uint8_t><<<ntiles, TILE_THREADS, 0, st>>>(px, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
                 else k_scatter<int16_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.cap, L.tile_hist, L.e_grp, L.gidx);
                 s.launched();
             }
