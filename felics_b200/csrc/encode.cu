@@ -1538,8 +1538,10 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                     ctx->walk_attr_done = true;
                 }
                 if (L.sp) {
-                    const size_t walk_smem = overlap ? (size_t)200 * 1024 : sizeof(WalkSmem<true>);
-                    unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, overlap ? 148 : 148 * 3);
+                    // ctx->walk_per_sm (FELICS_B200_WALK_PER_SM, experiment): 2 or 3 walkers per SM beside the speculation
+                    const unsigned per_sm = overlap ? std::min(3u, std::max(1u, ctx->walk_per_sm)) : 3u;
+                    const size_t walk_smem = overlap ? std::max(sizeof(WalkSmem<true>), (size_t)(200 / per_sm) * 1024) : sizeof(WalkSmem<true>);
+                    unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * per_sm);
                     k_walk<true><<<blocks, 32, walk_smem, wst>>>(wa);
                 } else {
                     unsigned blocks = (unsigned)std::min<size_t>(np * NBIN, 148 * 12);

@@ -1,8 +1,8 @@
 // 16-bit samples (traits.rs:35-43): K = {0..14}, MAX_CONTEXT = 131070, count scaling at 1024.
-// First correct device path for this pixel depth: the reference loops run as they are written
-// (compression.rs:76-148 / :151-248), one warp per image with lane 0 walking the raster, the
-// 131071 x 15 estimator table (parameter_selection.rs:29-33) split between shared and global memory.  Images of a batch
-// run in parallel; inside an image nothing is parallel yet (DESIGN.md "16-bit").
+// The serial 16-bit path: the reference loops run as they are written (compression.rs:76-148 / :151-248), one warp per
+// image with lane 0 walking the raster, the 131071 x 15 estimator table (parameter_selection.rs:29-33) split between
+// shared and global memory.  This is the DECODER (a file is one serial bit chain) and the cross-check encoder behind
+// FELICS_B200_SERIAL16; the product encoder is the parallel pipeline of enc16_par.cuh (DESIGN.md "16-bit").
 #pragma once
 #include <stdint.h>
 
