@@ -78,6 +78,10 @@ __device__ __forceinline__ void load4(const int16_t *p, int (&v)[4]) {
     const uint2 w = *reinterpret_cast<const uint2 *>(p);
     v[0] = (int)(int16_t)(w.x & 0xffffu); v[1] = (int)(int16_t)(w.x >> 16); v[2] = (int)(int16_t)(w.y & 0xffffu); v[3] = (int)(int16_t)(w.y >> 16);
 }
+__device__ __forceinline__ void load4(const int32_t *p, int (&v)[4]) {
+    const uint4 w = *reinterpret_cast<const uint4 *>(p);
+    v[0] = (int)w.x; v[1] = (int)w.y; v[2] = (int)w.z; v[3] = (int)w.w;
+}
 __device__ __forceinline__ PixelClass classify_from(int p, int v1, int v2) {   // compression.rs:118-145 given the two neighbours
     const int h = max(v1, v2), l = min(v1, v2);
     PixelClass r;

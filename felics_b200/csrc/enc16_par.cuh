@@ -211,9 +211,10 @@ __device__ __forceinline__ void bw16_pass128(const uint32_t (&e)[4], const bool 
         if (in[i]) kp[pix[i]] = (uint8_t)myk[i];
 }
 
-// Rows are independent, so four warps share a bucket: warp `way` takes the rows with (row & 3) == way.
+// Rows are independent, so two warps share a bucket: warp `way` takes the rows with (row & 1) == way.  (Four warps per
+// bucket halve the resident blocks at the wide pass's 235 registers: 1.36 vs 1.14 ms on the gray16 bench image.)
 constexpr uint32_t BW_SCAN_MIN_PER_ROW = 8;
-constexpr int BW_WAYS = 4;
+constexpr int BW_WAYS = 2;
 __global__ void __launch_bounds__(32 * BW_WAYS) k16_bwalk(const uint2 *__restrict__ grp, const uint32_t *__restrict__ chain_count,
                                                           const uint32_t *__restrict__ chain_base, const uint32_t *__restrict__ live,
                                                           uint32_t *__restrict__ counters, uint32_t cap, uint32_t npix,
@@ -236,24 +237,24 @@ __global__ void __launch_bounds__(32 * BW_WAYS) k16_bwalk(const uint2 *__restric
         uint8_t *kp = kpix + (size_t)p * npix;
         for (uint32_t j = threadIdx.x; j < ROWS16B * 16; j += 32 * BW_WAYS) (&tab[0][0])[j] = 0u;   // KEstimator::new: all counts zero
         __syncthreads();
-        const uint32_t waymask = (opts & 3u) == 0 ? 3u : ((opts & 3u) == 1 ? 1u : 0u);
+        const uint32_t waymask = (opts & 3u) == 0 ? (uint32_t)BW_WAYS - 1u : 0u;   // experiment switch: one warp takes every row
         if (way > waymask) { __syncthreads(); continue; }
         uint4 pa = make_uint4(0u, 0u, 0u, 0u), pb = pa;   // the next 128 elements, in flight while these are walked
         uint32_t pf = 0xffffffffu;
         for (uint32_t first = 0; first < count; first += 32) {
             if ((first & 127u) == 0 && first + 128 <= count && (opts & 8u) == 0) {
-                // 128 elements whose rows are all below 8 (contexts below 4096): at most two rows are mine, one wide pass each
+                // 128 elements whose rows are all below 8 (contexts below 4096): at most four rows are mine, one wide pass for each that occurs
                 const uint4 *s4 = reinterpret_cast<const uint4 *>(src + first) + 2 * lane;
                 uint4 ra = pa, rb = pb;
                 if (pf != first) { ra = s4[0]; rb = s4[1]; }
                 if (first + 256 <= count) { pa = s4[64]; pb = s4[65]; pf = first + 128; }
                 const uint32_t emask = (1u << E16_BITS) - 1u;
                 const uint32_t rows[4] = {ra.x >> E16_BITS, ra.z >> E16_BITS, rb.x >> E16_BITS, rb.z >> E16_BITS};
-                if (__reduce_or_sync(0xffffffffu, rows[0] | rows[1] | rows[2] | rows[3]) < 8u && waymask == 3u) {
+                if (__reduce_or_sync(0xffffffffu, rows[0] | rows[1] | rows[2] | rows[3]) < 8u && waymask == (uint32_t)BW_WAYS - 1u) {
                     const uint32_t e[4] = {ra.x & emask, ra.z & emask, rb.x & emask, rb.z & emask};
                     const uint32_t pix[4] = {ra.y, ra.w, rb.y, rb.w};
 #pragma unroll 1
-                    for (uint32_t prow = way; prow < 8u; prow += 4u) {
+                    for (uint32_t prow = way; prow < 8u; prow += (uint32_t)BW_WAYS) {
                         const bool in[4] = {rows[0] == prow, rows[1] == prow, rows[2] == prow, rows[3] == prow};
                         const uint32_t mybits = (in[0] ? e[0] : 0u) | (in[1] ? e[1] : 0u) | (in[2] ? e[2] : 0u) | (in[3] ? e[3] : 0u);
                         if (!__any_sync(0xffffffffu, in[0] || in[1] || in[2] || in[3])) continue;
@@ -385,22 +386,40 @@ __device__ __forceinline__ Code16 code16_of(const PixelClass &pc, const uint8_t 
     return c;
 }
 
-// bits per tile
+// bits per tile; QUADS (width a multiple of four): four consecutive samples per thread (classify4)
+template <bool QUADS>
 __global__ void __launch_bounds__(TILE_THREADS) k16_code(const int32_t *__restrict__ planes, uint32_t w, uint32_t npix, uint32_t tpp,
                                                          const uint8_t *__restrict__ kpix, uint32_t *__restrict__ tile_bits) {
     __shared__ uint32_t wsum[TILE_WARPS];
     const uint32_t bid = blockIdx.x;
     const uint32_t p = bid / tpp, t = bid - p * tpp;
     const uint8_t *kp = kpix + (size_t)p * npix;
+    const int32_t *pl = planes + (size_t)p * npix;
     uint32_t bits = 0;
     RasterCursor<int32_t> cur;
-    cur.init(planes + (size_t)p * npix, t * TILE + threadIdx.x, w);
+    if (QUADS) {
+        cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+#pragma unroll
+        for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
+            if (cur.i < npix) {
+                PixelClass pc[4];
+                bool valid[4];
+                classify4(pl, cur.i, cur.x, cur.y, w, pc, valid);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (valid[q]) bits += code16_of(pc[q], kp, cur.i + q).len;
+            }
+            cur.step(4 * TILE_THREADS);
+        }
+    } else {
+        cur.init(pl, t * TILE + threadIdx.x, w);
 #pragma unroll 4
-    for (int j = 0; j < TILE / TILE_THREADS; j++) {
-        const uint32_t i = cur.i;
-        if (i >= npix) break;
-        if (i >= 2) bits += code16_of(cur.classify(), kp, i).len;
-        cur.step(TILE_THREADS);
+        for (int j = 0; j < TILE / TILE_THREADS; j++) {
+            const uint32_t i = cur.i;
+            if (i >= npix) break;
+            if (i >= 2) bits += code16_of(cur.classify(), kp, i).len;
+            cur.step(TILE_THREADS);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
@@ -417,6 +436,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k16_code(const int32_t *__restri
 // Packing: a thread owns 16 consecutive pixels; lengths are scanned over the tile, codes are OR-ed into a shared-memory
 // image of the tile's bits (or straight into the arena when a tile is longer than the buffer: unary runs of 16-bit
 // residuals reach 131069 bits).
+template <bool QUADS>
 __global__ void __launch_bounds__(TILE_THREADS) k16_pack(PackArgs a, const int32_t *__restrict__ planes, uint32_t w,
                                                          const uint8_t *__restrict__ kpix) {
     __shared__ uint32_t buf[PACK_WORDS];
@@ -439,14 +459,32 @@ __global__ void __launch_bounds__(TILE_THREADS) k16_pack(PackArgs a, const int32
     Code16 c[WARP_ITERS];
     uint32_t mylen = 0;
     {
+        const int32_t *pl = planes + (size_t)p * a.npix;
         RasterCursor<int32_t> cur;
-        cur.init(planes + (size_t)p * a.npix, lstart, w);
+        cur.init(pl, lstart, w);
+        if (QUADS) {
 #pragma unroll
-        for (int it = 0; it < WARP_ITERS; it++) {
-            c[it].len = 0; c[it].pay = 0;
-            if (cur.i >= 2 && cur.i < a.npix) c[it] = code16_of(cur.classify(), kp, cur.i);
-            mylen += c[it].len;
-            cur.step(1);
+            for (int qd = 0; qd < WARP_ITERS / 4; qd++) {
+                PixelClass pc[4];
+                bool valid[4] = {false, false, false, false};
+                if (cur.i < a.npix) classify4(pl, cur.i, cur.x, cur.y, w, pc, valid);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int it = qd * 4 + q;
+                    c[it].len = 0; c[it].pay = 0;
+                    if (valid[q]) c[it] = code16_of(pc[q], kp, cur.i + q);
+                    mylen += c[it].len;
+                }
+                cur.step(4);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < WARP_ITERS; it++) {
+                c[it].len = 0; c[it].pay = 0;
+                if (cur.i >= 2 && cur.i < a.npix) c[it] = code16_of(cur.classify(), kp, cur.i);
+                mylen += c[it].len;
+                cur.step(1);
+            }
         }
     }
     uint32_t inc = mylen;
@@ -596,6 +634,7 @@ int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const
         L = carve16((uint8_t *)ctx->scratch, g, ni);
         const uint16_t *px = (const uint16_t *)((const uint8_t *)d_pixels + first * img_bytes);
         const unsigned ntiles = (unsigned)(np * g.tpp);
+        const bool quads = g.w % 4 == 0 && g.w >= 8 && !ctx->no_quads;   // the i32 planes are ours: always aligned
         FELICS_CUDA_TRY(cudaMemsetAsync(L.counters, 0, 8 * sizeof(uint32_t), st));
         if (g.npix > 0) {
             StageScope s(ctx, ST_PLANES);
@@ -609,7 +648,8 @@ int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const
             {
                 StageScope s(ctx, ST_HIST);
                 FELICS_CUDA_TRY(cudaMemsetAsync(L.chunk_tot, 0, np * g.nchunks * NBIN * sizeof(uint32_t), st));
-                k_hist<int32_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                if (quads) k_hist4<int32_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
+                else k_hist<int32_t><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, g.nchunks, L.tile_hist, L.chunk_tot);
                 s.launched();
             }
             {
@@ -635,7 +675,8 @@ int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const
             }
             {
                 StageScope s(ctx, ST_CODE);
-                k16_code<<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, L.kpix, L.tile_bits);
+                if (quads) k16_code<true><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, L.kpix, L.tile_bits);
+                else k16_code<false><<<ntiles, TILE_THREADS, 0, st>>>(L.planes, g.w, g.npix, g.tpp, L.kpix, L.tile_bits);
                 s.launched();
             }
         } else if (ntiles) {
@@ -677,7 +718,8 @@ int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const
             pa.rec = nullptr; pa.tile_bits = L.tile_bits; pa.tile_off = L.tile_off; pa.plane_bits = L.plane_bits; pa.img_off = L.img_off;
             pa.arena = (uint32_t *)target; pa.arena_byte0 = target_off; pa.npix = g.npix; pa.tpp = g.tpp; pa.nch = g.nch;
             if (ntiles && g.npix > 2) {
-                k16_pack<<<ntiles, TILE_THREADS, 0, st>>>(pa, L.planes, g.w, L.kpix);
+                if (quads) k16_pack<true><<<ntiles, TILE_THREADS, 0, st>>>(pa, L.planes, g.w, L.kpix);
+                else k16_pack<false><<<ntiles, TILE_THREADS, 0, st>>>(pa, L.planes, g.w, L.kpix);
                 s.launched();
             }
             k_heads<int32_t><<<(unsigned)((np + 127) / 128), 128, 0, st>>>(pa, L.planes, (uint32_t)np, g.w, g.h, hdr.color_type, hdr.pixel_depth);

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist4(const T *__restrict__ pl
             classify4(pl, cur.i, cur.x, cur.y, w, pc, valid);
 #pragma unroll
             for (int q = 0; q < 4; q++)
-                if (valid[q] && pc[q].cls != 0) atomicAdd(&h[pc[q].delta], 1u);
+                if (valid[q] && pc[q].cls != 0) atomicAdd(&h[sizeof(T) == 4 ? (pc[q].delta & (NBIN - 1)) : pc[q].delta], 1u);
         }
         cur.step(4 * TILE_THREADS);
     }
