@@ -435,3 +435,17 @@ def test_sidecar_rejects_foreign_or_damaged_side_files(codec):
         codec.compress_with_sidecar(gnat_image(333, 200), 3)
     with pytest.raises(felics_b200.FelicsError):                                 # 16-bit: no sidecar
         codec.compress_with_sidecar(np.zeros((64, 64), np.uint16))
+
+
+def test_16bit_serial_encoder_cross_check(monkeypatch):
+    # FELICS_B200_SERIAL16=1 selects the one-warp-per-image encoder (the reference loops as written): both device paths
+    # and the oracle must agree byte for byte
+    img = gnat16(257, 131, 90)
+    rgb = np.ascontiguousarray(np.stack([img, np.roll(img, 5, 1), img[::-1]], axis=-1))
+    monkeypatch.setenv("FELICS_B200_SERIAL16", "1")
+    with felics_b200.Codec(device=0) as serial:
+        monkeypatch.delenv("FELICS_B200_SERIAL16")
+        with felics_b200.Codec(device=0) as parallel:
+            for im in (img, rgb):
+                a, b = serial.compress(im), parallel.compress(im)
+                assert a == b == fo.compress(im)
