@@ -449,3 +449,27 @@ def test_16bit_serial_encoder_cross_check(monkeypatch):
             for im in (img, rgb):
                 a, b = serial.compress(im), parallel.compress(im)
                 assert a == b == fo.compress(im)
+
+
+def test_sidecar_random_shapes(codec):
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=12, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+    @given(st.sampled_from([8, 64, 256, 512, 1024, 2048, 4096]), st.integers(3, 700), st.booleans(), st.integers(0, 2**31 - 1),
+           st.sampled_from([0, 2, 30]), st.integers(1, 6))
+    def run(width, height, rgb, seed, noise, mult):
+        rng = np.random.default_rng(seed)
+        height = max(height, 8192 // width + 3)                      # more than two tiles, so that several bands exist
+        shape = (height, width, 3) if rgb else (height, width)
+        yy, xx = np.mgrid[0:height, 0:width]
+        base = 128 + 90 * np.sin(xx / 23.0) * np.cos(yy / 31.0)
+        if rgb:
+            base = np.stack([base, 255 - base, np.roll(base, 7, 0)], axis=-1)
+        img = np.clip(base + (rng.integers(-noise, noise + 1, shape) if noise else 0), 0, 255).astype(np.uint8)
+        unit = 4096 // np.gcd(width, 4096)
+        rows = int(unit * mult) if unit * mult >= 2 else 2
+        fel, side = codec.compress_with_sidecar(img, rows)
+        assert fel == fo.compress(img)
+        assert np.array_equal(codec.decompress_with_sidecar(fel, side), img), (shape, rows)
+
+    run()
