@@ -738,7 +738,8 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
                 }
                 hop_fails++;
                 hops_refused++;
-                hop_skip = seg + 1 + (hop_fails >= 2 ? (1u << min(hop_fails - 2u, 6u)) : 0u);   // back off: 1, 2, 4, .. 64 segments
+                // back off: 1, 2, 4, .. segments; up to 64 for a chain that has never hopped (it flips all the time), up to 8 otherwise
+                hop_skip = seg + 1 + (hop_fails >= 2 ? (1u << min(hop_fails - 2u, hops_done ? 3u : 6u)) : 0u);
             }
             // ---- stream mode: walk window w element-exactly ----
             {
