@@ -118,6 +118,8 @@ int felics_ctx_create(int device, felics_ctx **out) {
         ctx->no_spec = ns && ns[0] == '1';
         const char *s16 = getenv("FELICS_B200_SERIAL16");   // debug switch: serial 16-bit encoder
         ctx->serial16 = s16 && s16[0] == '1';
+        const char *eh = getenv("FELICS_B200_EARLY_HOPS");
+        ctx->early_hops = eh && eh[0] == '1';
         const char *wp = getenv("FELICS_B200_WALK_PER_SM");
         if (wp) ctx->walk_per_sm = (unsigned)strtoul(wp, nullptr, 0);
         const char *nq = getenv("FELICS_B200_NO_QUADS");

@@ -85,6 +85,7 @@ struct felics_ctx {
     bool no_hop = false;          // debug switch: no segment hops in the serial walker
     bool no_spec = false;         // debug/bench switch: skip the speculative walk
     uint32_t bw16_opts = 0;       // experiment switches of the 16-bit bucket walk (FELICS_B200_BW16)
+    bool early_hops = false;      // experiment: hop tables for every planned chain, built before the speculative walk
     unsigned walk_per_sm = 1;     // walker blocks per SM while the speculative kernels run beside them
     bool no_quads = false;        // debug switch: one sample per thread in the histogram / code kernels
     bool serial16 = false;        // debug switch: the one-warp-per-image 16-bit encoder instead of the parallel one

@@ -554,6 +554,7 @@ struct WalkArgs {
     HopTables hop;           // segment hops for rejected chains (hop.ready == nullptr: off)
     const SpDesc *desc;
     const uint32_t *chain_fail;
+    uint32_t hop_any = 0;    // hop over any planned chain, without waiting for the speculation's verdict (experiment)
 };
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(32) k_walk(WalkArgs a) {
             if (FINE && ready == 1 && !hop_on) {
                 ready = 2;
                 const uint32_t di = a.hop.pc2desc[pc];
-                if (di != 0xFFFFFFFFu && *reinterpret_cast<const volatile uint32_t *>(a.chain_fail + di) == SP_OK - 1) {
+                if (di != 0xFFFFFFFFu && (a.hop_any || *reinterpret_cast<const volatile uint32_t *>(a.chain_fail + di) == SP_OK - 1)) {
                     hop_on = true;
                     hop_seg0 = a.desc[di].seg0;
                     hop_skip = (w >> 2) + 1;   // first attempt at the next segment boundary
@@ -1528,6 +1529,7 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 wa.resolved = L.sp_resolved;
                 wa.hop = L.hop; wa.desc = L.sp_desc; wa.chain_fail = L.sp_chain_fail;
                 if (!hops) wa.hop.ready = nullptr;
+                wa.hop_any = hops && ctx->early_hops;
                 wa.fine = L.fine; wa.e_grp = L.e_grp; wa.blk_rec4 = (const uint4 *)L.blk_rec;
                 wa.chain_count = L.chain_count; wa.chain_base = L.chain_base; wa.live = L.live;
                 wa.counters = L.counters; wa.ep_rec = (uint4 *)L.ep_rec; wa.blk_epoch = L.blk_epoch;
@@ -1571,6 +1573,17 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 }
                 const SpSizes &z = L.spsz;
                 k_sp_plan<<<1, NBIN, 0, st>>>(sa);
+                const bool early = hops && ctx->early_hops;   // experiment: hop tables of every planned chain first
+                if (hops && !ctx->hop_attr_done) {
+                    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_hop_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HopSmem)));
+                    ctx->hop_attr_done = true;
+                }
+                if (early) {
+                    sa.hop_all = 1;
+                    k_hop_maps<<<z.max_seg, 1024, sizeof(HopSmem), st>>>(sa, L.hop);
+                    k_hop_ready<<<1, 1, 0, st>>>(L.hop);
+                    s.launched(2);
+                }
                 k_sp_maps<<<z.max_seg, 1024, sizeof(SpSegSmem), st>>>(sa);
                 k_sp_compose<<<z.max_grp, 1024, 0, st>>>(sa);
                 k_sp_scan<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
@@ -1580,13 +1593,9 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
                 k_sp_finish<true><<<(z.max_eb + 3) / 4, 128, 0, st>>>(sa);
                 k_sp_resolve<<<(z.max_desc + 63) / 64, 64, 0, st>>>(sa);
                 s.launched(9);
-                if (hops) {
+                if (hops && !early) {
                     // tables for segment hops over the chains that failed the verification; the walker (already running
                     // on the other stream) starts using them when the ready flag appears
-                    if (!ctx->hop_attr_done) {
-                        FELICS_CUDA_TRY(cudaFuncSetAttribute(k_hop_maps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HopSmem)));
-                        ctx->hop_attr_done = true;
-                    }
                     k_hop_maps<<<z.max_seg, 1024, sizeof(HopSmem), st>>>(sa, L.hop);
                     k_hop_ready<<<1, 1, 0, st>>>(L.hop);
                     s.launched(2);

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(1024, 1) k_hop_maps(SpArgs a, HopTables h) {
     const uint32_t slot = blockIdx.x;
     if (slot >= a.counts[1]) return;
     const uint32_t di = a.seg_desc[slot];
-    if (a.chain_fail[di] != SP_OK - 1) return;     // only chains that failed the verification
+    if (!a.hop_all && a.chain_fail[di] != SP_OK - 1) return;     // only chains that failed the verification
     const SpDesc d = a.desc[di];
     const uint32_t seg = slot - d.seg0;
     const uint32_t e0 = seg * SP_SEG;

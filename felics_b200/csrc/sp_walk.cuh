@@ -67,6 +67,7 @@ struct SpArgs {
     uint8_t *resolved;          // [plane*512 + context]: 1 when the chain needs no serial walk
     uint32_t *dbg;              // encode counters: [3] chains tried, [4] chains resolved
     uint32_t *pc2desc;          // [plane*512 + context] -> descriptor index (may be null)
+    uint32_t hop_all = 0;       // hop tables for every planned chain, before the verification has a verdict (experiment)
     uint32_t np, cap, epcap;
     SpSizes sz;
 };
