@@ -868,6 +868,14 @@ __global__ void __launch_bounds__(256, 4) k_kfill(const uint16_t *__restrict__ e
     uint32_t ep = blk_epoch[blk];
     uint4 b0 = ep_rec[(size_t)ep * 2], b1 = ep_rec[(size_t)ep * 2 + 1];
     uint32_t next = ep_rec[(size_t)ep * 2 + 3].z;   // first element of the following epoch (0xFFFFFFFF after the last one)
+    // A counter x travels as the key x * 8 + (5 - k): the smallest key is the smallest count with ties going to the largest
+    // k, i.e. get_k's `<=` scan (parameter_selection.rs:78-83).  Counts stay far below 2^28, so the key fits.
+    uint32_t key[NK];
+    auto rekey = [&]() {
+        key[0] = (b0.x + q[0]) * 8u + 5u; key[1] = (b0.y + q[1]) * 8u + 4u; key[2] = (b0.z + q[2]) * 8u + 3u;
+        key[3] = (b0.w + q[3]) * 8u + 2u; key[4] = (b1.x + q[4]) * 8u + 1u; key[5] = (b1.y + q[5]) * 8u;
+    };
+    rekey();
     uint32_t kk[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -876,10 +884,12 @@ __global__ void __launch_bounds__(256, 4) k_kfill(const uint16_t *__restrict__ e
             ep++;
             b0 = ep_rec[(size_t)ep * 2]; b1 = ep_rec[(size_t)ep * 2 + 1];
             next = ep_rec[(size_t)ep * 2 + 3].z;
+            rekey();
         }
-        const uint32_t v[NK] = {b0.x + q[0] + (x01[i] & 0xffffu), b0.y + q[1] + (x01[i] >> 16), b0.z + q[2] + (x23[i] & 0xffffu),
-                                b0.w + q[3] + (x23[i] >> 16), b1.x + q[4] + (x45[i] & 0xffffu), b1.y + q[5] + (x45[i] >> 16)};
-        kk[i] = (uint32_t)argmin_last(v);
+        const uint32_t m = min(min(min(key[0] + ((x01[i] & 0xffffu) << 3), key[1] + ((x01[i] >> 16) << 3)),
+                                   min(key[2] + ((x23[i] & 0xffffu) << 3), key[3] + ((x23[i] >> 16) << 3))),
+                               min(key[4] + ((x45[i] & 0xffffu) << 3), key[5] + ((x45[i] >> 16) << 3)));
+        kk[i] = 5u - (m & 7u);
     }
     uint2 out;
     out.x = kk[0] | (kk[1] << 8) | (kk[2] << 16) | (kk[3] << 24);
