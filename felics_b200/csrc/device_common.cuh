@@ -44,6 +44,12 @@ struct RasterCursor {
             y = i / w; x = i - y * w;
         }
     }
+    // the same step with its quotient and remainder by the width worked out once (q = s / w, r = s % w): no division per step
+    __device__ __forceinline__ void step_qr(uint32_t s, uint32_t q, uint32_t r) {
+        i += s; pp += s;
+        y += q; x += r;
+        if (x >= w) { x -= w; y++; }
+    }
     // neighbours and class of the sample under the cursor (misc.rs:6-24, compression.rs:118-145); needs i >= 2
     __device__ __forceinline__ PixelClass classify() const {
         const int p = pp[0];

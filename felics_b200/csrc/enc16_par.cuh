@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k16_code(const int32_t *__restri
     RasterCursor<int32_t> cur;
     if (QUADS) {
         cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+        const uint32_t step_q = (4u * TILE_THREADS) / w, step_r = (4u * TILE_THREADS) - step_q * w;
 #pragma unroll
         for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
             if (cur.i < npix) {
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k16_code(const int32_t *__restri
                 for (int q = 0; q < 4; q++)
                     if (valid[q]) bits += code16_of(pc[q], kp, cur.i + q).len;
             }
-            cur.step(4 * TILE_THREADS);
+            cur.step_qr(4 * TILE_THREADS, step_q, step_r);
         }
     } else {
         cur.init(pl, t * TILE + threadIdx.x, w);

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist4(const T *__restrict__ pl
     const T *pl = planes + (size_t)p * npix;
     RasterCursor<T> cur;
     cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+    const uint32_t step_q = (4u * TILE_THREADS) / w, step_r = (4u * TILE_THREADS) - step_q * w;
 #pragma unroll
     for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
         if (cur.i < npix) {
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_hist4(const T *__restrict__ pl
             for (int q = 0; q < 4; q++)
                 if (valid[q] && pc[q].cls != 0) atomicAdd(&h[sizeof(T) == 4 ? (pc[q].delta & (NBIN - 1)) : pc[q].delta], 1u);
         }
-        cur.step(4 * TILE_THREADS);
+        cur.step_qr(4 * TILE_THREADS, step_q, step_r);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < NBIN; c += TILE_THREADS) {
@@ -972,6 +973,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code4(const T *__restrict__ pl
     uint32_t bits = 0;
     RasterCursor<T> cur;
     cur.init(pl, t * TILE + 4u * threadIdx.x, w);
+    const uint32_t step_q = (4u * TILE_THREADS) / w, step_r = (4u * TILE_THREADS) - step_q * w;
 #pragma unroll
     for (int j = 0; j < TILE / (4 * TILE_THREADS); j++) {
         const uint32_t i = cur.i;
@@ -989,7 +991,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_code4(const T *__restrict__ pl
             }
             *reinterpret_cast<uint4 *>(rec + (size_t)p * npix + i) = make_uint4(r[0], r[1], r[2], r[3]);   // npix and i are multiples of four
         }
-        cur.step(4 * TILE_THREADS);
+        cur.step_qr(4 * TILE_THREADS, step_q, step_r);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, o);
