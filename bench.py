@@ -4,16 +4,17 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
   python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU implementation (oracle port) on host cores
 
-Workload (BASELINE.json configs[1]): one synthetic 8192x8192 8-bit grayscale image per GPU
-(generator "G-nat"; seed 2 + rank).  A step = one encode of that image.  A single
-image cannot be split bit-exactly (one estimator and one bit chain per plane), so N GPUs run N
-independent replicas: weak scaling, value = all ranks' pixels / max-over-ranks time.
-`--workload tiles` switches to BASELINE.json configs[3]-style batches of 512x512 tiles (our own
-measurements; the driver's line is the default workload).
+Default workload = BASELINE.json configs[3]: a batch of 65,536 synthetic 512x512 gray8 tiles (16 GiB; integer generator of
+SURVEY.md 8(d) item 4, generated ON THE DEVICE by felics_debug_generate_tiles, numpy twin felics_b200/synth.py), sharded
+in contiguous ranges over the ranks (felics_b200.sharding.shard_range): STRONG scaling, the batch is the same at every N and
+N = 1 holds all of it.  A step = one encode of the rank's whole shard; value = 65,536 tiles' pixels / max-over-ranks time.
+The per-image sizes are gathered over NCCL (sharding.gather_sizes) -- the only exchange -- and >= 256 sampled tiles per rank
+are compared with the CPU oracle.  `--workload image|rgb|gray16` select the single-image configs (configs[1], configs[2],
+SURVEY 8(f)1: independent replicas per GPU, weak scaling); the default run reports them as extra keys (`other_configs`).
 
-value : whole-job encode MPixel/s with the image already resident in HBM (device entry point)
-e2e   : the same through the host-memory C ABI call (felics_compress): H2D of the pixels from
-        pinned host memory and D2H of the .fel bytes inside the timed region
+value : whole-job encode MPixel/s with the input already resident in HBM (device entry point)
+e2e   : the same through the host-memory C ABI call (felics_compress_batch): H2D of the pixels from pinned host memory and
+        D2H of the .fel bytes inside the timed region
 """
 from __future__ import annotations
 
@@ -31,6 +32,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+
+from felics_b200.synth import tile_batch  # noqa: E402  (numpy twin of the device tile generator)
 
 W2, H2 = 8192, 8192
 TILE_W = TILE_H = 512
@@ -63,27 +66,6 @@ def gnat16_image(width, height, seed=2):
         v = 256 * (128 + 60 * np.sin(x / 97) * np.cos(y / 131) + 40 * np.sin((x + y) / 37)) + rng.normal(0, 192, (len(y), width))
         out[y0:y0 + len(y)] = np.clip(np.rint(v), 0, 65535).astype(np.uint16)
     return out
-
-
-def tile_batch(n, first=0, seed=1):
-    """SURVEY.md 8(d) config 4 integer generator (numpy twin): tile t, pixel (x, y)."""
-    t = (np.arange(first, first + n, dtype=np.uint64))[:, None, None]
-    y = np.arange(TILE_H, dtype=np.uint64)[None, :, None]
-    x = np.arange(TILE_W, dtype=np.uint64)[None, None, :]
-
-    def tri(u, p):
-        return p - np.abs((u % (2 * p)).astype(np.int64) - p)
-
-    base = 96 + 64 * tri(x + 37 * t, 256) // 256 + 64 * tri(y + 53 * t, 384) // 384
-    z = (np.uint64(seed) ^ (t << np.uint64(40)) ^ (y << np.uint64(20)) ^ x) + np.uint64(0x9E3779B97F4A7C15)
-    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    z = z ^ (z >> np.uint64(31))
-    bits = (z & np.uint64(0xFFFF)).astype(np.uint32)
-    pop = np.zeros(bits.shape, np.int64)
-    for i in range(16):
-        pop += (bits >> i) & 1
-    return np.clip(base + pop - 8, 0, 255).astype(np.uint8)
 
 
 class ClockSampler:
@@ -152,14 +134,61 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel):
+def recorded_traffic(kernel, workload):
+    """dram bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/traffic.json
+    names the capture, its command and the git revision it was taken at); None when there is no capture."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(kernel)
+            return json.loads(p.read_text()).get(workload, {}).get(kernel)
         except Exception:
             return None
     return None
+
+
+TOTAL_TILES = 65536
+W3, H3 = 7680, 4320
+
+
+def gnat_rgb(width, height, rank=0):
+    """SURVEY.md 8(d) config 3: three G-nat planes, phases (0, 11, 23) px, seeds 3, 4, 5 (+3*rank), interleaved R, G, B."""
+    return np.stack([gnat_image(width, height, seed=s + 3 * rank, phase=p) for s, p in ((3, 0), (4, 11), (5, 23))], axis=-1)
+
+
+def workload_name(args):
+    if args.workload == "rgb":
+        return "configs[2]: one synthetic 7680x4320 8-bit RGB frame (three G-nat planes, YCoCg-R inside the timed path) per GPU, encode"
+    if args.workload == "gray16":
+        return "SURVEY 8(f)1: one synthetic 4096x4096 gray16 image (G-nat x 256, noise sigma 192, seed 2+rank) per GPU, encode"
+    if args.workload == "image":
+        return "configs[1]: one synthetic 8192x8192 gray8 image (G-nat, seed 2+rank) per GPU, encode"
+    return (f"configs[3]: batch of {args.tiles} synthetic 512x512 gray8 tiles (integer generator, seed 1), contiguous shards over the GPUs, encode")
+
+
+def cpu_info():
+    model = None
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count() or 1, "cpu_model": model}
+
+
+def cpu_tiles_rate(fo, tiles, threads):
+    """Oracle port on `threads` host threads, one image per thread at a time (ctypes releases the GIL): MPixel/s."""
+    n = len(tiles)
+    threads = max(1, min(threads, n))
+    bounds = [n * i // threads for i in range(threads + 1)]
+    ts = [threading.Thread(target=fo.compress_many, args=(tiles[bounds[i]:bounds[i + 1]], 0, 0, TILE_W, TILE_H)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return tiles.size / (time.perf_counter() - t0) / 1e6
 
 
 # ----------------------------------------------------------------------------------------------
@@ -173,44 +202,43 @@ def run_reference(args):
     fo.lib()
     n = args.gpus
     cores = os.cpu_count() or 1
-    threads = min(n, cores)
+    info = cpu_info()
     if args.workload == "tiles":
-        per = 64  # bounded sample: 64 tiles per replica
-        imgs = [tile_batch(per, first=r * args.tiles) for r in range(n)]
-        sample = f"{per} of {args.tiles} 512x512 tiles per replica, {n} replica(s), one image per thread"
-        px_per_step = per * TILE_W * TILE_H * n
-    elif args.workload == "gray16":
-        rows = 2048
-        imgs = [gnat16_image(W16, rows, seed=2 + r) for r in range(n)]
-        sample = f"top {rows} rows (4096x{rows}) of each replica's 4096x4096 gray16 image, {n} replica(s), one image per thread"
-        px_per_step = W16 * rows * n
-    elif args.workload == "rgb":
-        rows = 1024  # bounded sample: the top 1024 rows of each replica's frame (7.9 MPixel, 23.6 MSample)
-        imgs = [gnat_rgb(W3, rows, rank=r) for r in range(n)]
-        sample = f"top {rows} rows (7680x{rows}) of each replica's 7680x4320 RGB frame, {n} replica(s), one image per thread"
-        px_per_step = W3 * rows * n
+        # bounded sample of the batch: its first 1024 tiles per step, on all host threads (images are independent units in
+        # the reference too: tests/compress.rs:15-35 loops over files)
+        ns = min(1024, args.tiles)
+        imgs = np.concatenate([tile_batch(min(64, ns - s0), first=s0) for s0 in range(0, ns, 64)])
+        threads = min(cores, ns)
+        sample = f"first {ns} of the {args.tiles} tiles per step, {threads} threads, one image per thread at a time"
+        px_per_step = imgs.size
+
+        def step():
+            t0 = time.perf_counter()
+            cpu_tiles_rate(fo, imgs, threads)
+            return time.perf_counter() - t0
     else:
-        rows = 2048  # bounded sample: the top 2048 rows of each replica's image (16.8 MPixel)
-        imgs = [gnat_image(W2, rows, seed=2 + r) for r in range(n)]
-        sample = f"top {rows} rows (8192x{rows}) of each replica's 8192x8192 image, {n} replica(s), one image per thread"
-        px_per_step = W2 * rows * n
-
-    def work(i):
-        if args.workload == "tiles":
-            fo.compress_many(imgs[i], 0, 0, TILE_W, TILE_H)
+        # single-image configs: the whole image (a single image is serial in the reference), one replica per GPU of our arm
+        if args.workload == "gray16":
+            imgs = [gnat16_image(W16, H16, seed=2 + r) for r in range(n)]
+            px_per_step = W16 * H16 * n
+        elif args.workload == "rgb":
+            imgs = [gnat_rgb(W3, H3, rank=r) for r in range(n)]
+            px_per_step = W3 * H3 * n
         else:
-            fo.compress(imgs[i])
+            imgs = [gnat_image(W2, H2, seed=2 + r) for r in range(n)]
+            px_per_step = W2 * H2 * n
+        threads = min(n, cores)
+        sample = f"the whole image of each of the {n} replica(s), one image per thread ({threads} threads)"
 
-    def step():
-        ts = [threading.Thread(target=work, args=(i,)) for i in range(n)]
-        t0 = time.perf_counter()
-        # ctypes releases the GIL: replicas run on separate cores (at most `cores` at once)
-        for batch in range(0, n, threads):
-            for t in ts[batch:batch + threads]:
-                t.start()
-            for t in ts[batch:batch + threads]:
-                t.join()
-        return time.perf_counter() - t0
+        def step():
+            ts = [threading.Thread(target=fo.compress, args=(imgs[i],)) for i in range(n)]
+            t0 = time.perf_counter()
+            for b0 in range(0, n, threads):
+                for t in ts[b0:b0 + threads]:
+                    t.start()
+                for t in ts[b0:b0 + threads]:
+                    t.join()
+            return time.perf_counter() - t0
 
     for _ in range(args.warmup):
         step()
@@ -219,70 +247,292 @@ def run_reference(args):
     value = px_per_step * args.steps / total / 1e6
     line = {
         "impl": "reference", "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": n, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "tiles" else "weak",
         "vs_baseline": None, "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "MPixel/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of the reference's Rust loops (no Rust toolchain in the image); a single image is serial in the reference"},
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": value, "unit": "MPixel/s", "cores": threads, "kind": "port", "sample": sample, **info,
+                         "note": "C restatement of the reference's Rust loops (no Rust toolchain in the image)"},
         "e2e": {"value": value, "unit": "MPixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def gnat_rgb(width, height, rank=0):
-    """SURVEY.md 8(d) config 3: three G-nat planes, phases (0, 11, 23) px, seeds 3, 4, 5 (+3*rank), interleaved R, G, B."""
-    return np.stack([gnat_image(width, height, seed=s + 3 * rank, phase=p) for s, p in ((3, 0), (4, 11), (5, 23))], axis=-1)
-
-
-W3, H3 = 7680, 4320
-
-
-def workload_name(args):
-    if args.workload == "rgb":
-        return "configs[2]: one synthetic 7680x4320 8-bit RGB frame (three G-nat planes, YCoCg-R inside the timed path) per GPU, encode"
-    if args.workload == "gray16":
-        return "SURVEY 8(f)1: one synthetic 4096x4096 gray16 image (G-nat x 256, noise sigma 192, seed 2+rank) per GPU, encode"
-    if args.workload == "tiles":
-        return f"configs[3]-style: {args.tiles} synthetic 512x512 gray8 tiles per GPU (integer generator, seed 1), encode"
-    return "configs[1]: one synthetic 8192x8192 gray8 image (G-nat, seed 2+rank) per GPU, encode"
-
-
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    import felics_b200
+class Rig:
+    """Device, codec and timing helpers shared by the workloads."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        import felics_b200
+        self.torch, self.dist, self.fb = torch, dist, felics_b200
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.codec = felics_b200.Codec(device=self.local)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.codec.set_stream(self.stream.cuda_stream)
+        self.lib = felics_b200.load_library()
 
-    if args.workload == "tiles":
-        n_img = args.tiles
-        chunk = 256
-        host = np.concatenate([tile_batch(min(chunk, n_img - s), first=rank * n_img + s) for s in range(0, n_img, chunk)])
-        hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, TILE_W, TILE_H)
-    elif args.workload == "gray16":
-        n_img = 1
-        host = gnat16_image(W16, H16, seed=2 + rank)[None]
-        hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Sixteen, W16, H16)
-    elif args.workload == "rgb":
-        n_img = 1
-        host = gnat_rgb(W3, H3, rank=rank)[None]
-        hdr = felics_b200.Header(felics_b200.ColorType.Rgb, felics_b200.PixelDepth.Eight, W3, H3)
-    else:
-        n_img = 1
-        host = gnat_image(W2, H2, seed=2 + rank)[None]
-        hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, W2, H2)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps, flush=None):
+        """K steps, each bracketed by CUDA events on the launching stream (optionally an L2 flush before each)."""
+        torch = self.torch
+        ms = []
+        for _ in range(steps):
+            if flush is not None:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(self.dev)
+            a.record(self.stream)
+            fn()
+            b.record(self.stream)
+            torch.cuda.synchronize(self.dev)
+            ms.append(a.elapsed_time(b))
+        return ms
+
+    def reduce(self, x, op):
+        from felics_b200 import sharding
+        return sharding.reduce_scalar(x, op, device=self.dev)
+
+    def pinned(self, nbytes):
+        return self.torch.empty(nbytes, dtype=self.torch.uint8).pin_memory()
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def encode_host_call(rig, n_img, pin_in, chdr, pin_out, cap, host_offsets):
+    import ctypes as C
+    rc = rig.lib.felics_compress_batch(rig.codec._h, n_img, C.c_void_p(pin_in.data_ptr()), C.byref(chdr), C.c_void_p(pin_out.data_ptr()), cap,
+                                       host_offsets.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc:
+        raise RuntimeError(f"felics_compress_batch failed: {rc} {rig.lib.felics_last_error().decode()}")
+
+
+def roofline_of(stages, steps, alg_bytes_per_step, total_ms, workload):
+    peak, peak_src = measured_peak_gbs()
+    dom = max(stages, key=lambda k: stages[k][0])
+    dom_ms, dom_launches = stages[dom]
+    launches_per_step = max(dom_launches / max(steps, 1), 1.0)   # batches larger than the scratch budget run in several sub-batches
+    dom_avg_ms = dom_ms / max(dom_launches, 1)
+    per_launch = alg_bytes_per_step / launches_per_step
+    achieved = per_launch / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    whole = alg_bytes_per_step * steps / (total_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": recorded_traffic(dom, workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+            "kernel_ms_per_launch": dom_avg_ms, "kernel_launches_per_step": launches_per_step, "whole_encode_achieved_gbs": whole,
+            "whole_encode_frac": whole / peak}
+
+
+# ---- configs[3]: the sharded tile batch ---------------------------------------------------------
+def run_tiles(args, rig):
+    import ctypes as C
+    torch, fb, codec = rig.torch, rig.fb, rig.codec
+    from felics_b200 import sharding
+    from oracle import felics_oracle as fo
+
+    total = args.tiles
+    first, count = sharding.shard_range(total, rig.rank, rig.world)
+    tile_px = TILE_W * TILE_H
+    in_bytes = count * tile_px
+    hdr = fb.Header(fb.ColorType.Gray, fb.PixelDepth.Eight, TILE_W, TILE_H)
+    chdr = fb._c_header(hdr)
+    d_in = torch.empty(max(in_bytes, 16), dtype=torch.uint8, device=rig.dev)
+    codec.generate_tiles(d_in.data_ptr(), first, count)                     # on the device; numpy twin checked below
+    torch.cuda.synchronize(rig.dev)
+    for t in sorted({0, count // 2, count - 1}) if count else []:
+        assert np.array_equal(d_in[t * tile_px:(t + 1) * tile_px].cpu().numpy().reshape(TILE_H, TILE_W), tile_batch(1, first=first + t)[0]), \
+            "device generator and its numpy twin disagree"
+    cap = in_bytes * 5 // 8 + 4096 * max(count, 1)
+    d_out = torch.empty(cap, dtype=torch.uint8, device=rig.dev)
+
+    def encode_device():
+        return codec.compress_batch_device(count, d_in.data_ptr(), hdr, d_out.data_ptr(), cap)
+
+    sampler = ClockSampler(rig.local)
+    sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        offsets = encode_device()
+    fel_bytes = int(offsets[count])
+
+    codec.profile(True)
+    rig.barrier()
+    sampler.mark()
+    t_wall0 = time.perf_counter()
+    ms_dev = rig.timed(encode_device, args.steps)          # the shard (>= 2 GiB at N <= 8) and its output exceed the 126 MB L2
+    wall_dev = time.perf_counter() - t_wall0
+    rig.barrier()
+    stages = codec.stage_times()
+    launches = codec.total_launches()
+    codec.profile(False)
+
+    # the only exchange of the job: per-image sizes, gathered over the process group (NCCL under torchrun)
+    all_sizes = sharding.gather_sizes(np.diff(offsets.astype(np.int64)))
+    global_off = sharding.global_offsets(all_sizes)
+    assert len(all_sizes) == total and int(global_off[first]) + fel_bytes == int(global_off[first + count])
+
+    # parity: >= 256 sampled tiles of this rank's shard against the CPU oracle (bit-exact .fel bytes)
+    mismatches = 0
+    checked = 0
+    if args.verify and count:
+        idx = np.unique(np.linspace(0, count - 1, min(count, max(args.parity_tiles, 1))).astype(np.int64))
+        for i in idx:
+            got = d_out[int(offsets[i]):int(offsets[i + 1])].cpu().numpy().tobytes()
+            want = fo.compress(d_in[i * tile_px:(i + 1) * tile_px].cpu().numpy().reshape(TILE_H, TILE_W))
+            mismatches += got != want
+            checked += 1
+
+    # decode of the same shard as one batch (reported, not the target)
+    decode = None
+    if args.decode and count:
+        d_pix = torch.empty(in_bytes, dtype=torch.uint8, device=rig.dev)
+        codec.profile(True)
+        status = codec.decompress_batch_device(count, d_out.data_ptr(), offsets, hdr, d_pix.data_ptr())
+        torch.cuda.synchronize(rig.dev)
+        dst = codec.stage_times()
+        codec.profile(False)
+        dec_ms = dst["decode"][0] + dst["unplane"][0]
+        lossless = bool((not status.any()) and torch.equal(d_pix, d_in[:in_bytes]))
+        del d_pix
+        decode = (dec_ms, lossless)
+
+    # end to end through the host-memory C ABI call: pinned host pixels in, pinned host arena out.  The whole shard if the
+    # host can pin it, otherwise the largest power-of-two part that it can.
+    e2e_tiles = count
+    pin_in = pin_out = None
+    while e2e_tiles:
+        try:
+            pin_in = rig.pinned(e2e_tiles * tile_px)
+            pin_out = rig.pinned(e2e_tiles * tile_px * 5 // 8 + 4096 * e2e_tiles)
+            break
+        except RuntimeError:
+            pin_in = pin_out = None
+            e2e_tiles //= 2
+    ms_e2e, e2e_fel = [0.0], 0
+    if e2e_tiles:
+        pin_in.copy_(d_in[:e2e_tiles * tile_px])
+        host_offsets = np.zeros(e2e_tiles + 1, dtype=np.uint64)
+        e2e_steps = args.steps if e2e_tiles * tile_px <= (4 << 30) else min(args.steps, 3)
+        for _ in range(max(1, min(args.warmup, 2))):
+            encode_host_call(rig, e2e_tiles, pin_in, chdr, pin_out, pin_out.numel(), host_offsets)
+        rig.barrier()
+        ms_e2e = rig.timed(lambda: encode_host_call(rig, e2e_tiles, pin_in, chdr, pin_out, pin_out.numel(), host_offsets), e2e_steps)
+        rig.barrier()
+        e2e_fel = int(host_offsets[e2e_tiles])
+        if args.verify:
+            mismatches += not np.array_equal(pin_out[:int(host_offsets[1])].numpy(), d_out[:int(offsets[1])].cpu().numpy())
+            mismatches += int(host_offsets[e2e_tiles]) != int(offsets[e2e_tiles])
+    clocks = sampler.stop()
+
+    tot_dev_ms = rig.reduce(sum(ms_dev), "max")
+    e2e_rate_local = e2e_tiles * tile_px * len(ms_e2e) / (sum(ms_e2e) * 1e-3) / 1e6 if e2e_tiles and sum(ms_e2e) > 0 else 0.0
+    # every rank pushes its part through the same host at the same time: the job's end-to-end rate is what all ranks move
+    # over the slowest rank's time, normalised to the tiles the ranks actually pushed
+    e2e_px = rig.reduce(float(e2e_tiles * tile_px), "sum")
+    e2e_ms = rig.reduce(sum(ms_e2e) / max(len(ms_e2e), 1), "max")
+    all_pixels = rig.reduce(float(count * tile_px), "sum")
+    all_fel = rig.reduce(float(fel_bytes), "sum")
+    bad = rig.reduce(float(mismatches), "sum")
+    n_checked = rig.reduce(float(checked), "sum")
+    dec_ms = rig.reduce(decode[0], "max") if decode else None
+    dec_bad = rig.reduce(0.0 if (decode is None or decode[1]) else 1.0, "sum")
+
+    line = None
+    if rig.rank == 0:
+        enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane") and v[1]}
+        roof = roofline_of(enc_stages, args.steps, in_bytes + fel_bytes, sum(ms_dev), "tiles")
+        # CPU baseline on this box's host cores: the oracle port on a bounded sample of the same tiles
+        info = cpu_info()
+        n1 = min(count, 256)
+        t1 = d_in[:n1 * tile_px].cpu().numpy().reshape(n1, TILE_H, TILE_W)
+        one = cpu_tiles_rate(fo, t1, 1)
+        nall = min(count, 128 * info["nproc"], 4096)
+        tall = d_in[:nall * tile_px].cpu().numpy().reshape(nall, TILE_H, TILE_W)
+        allc = cpu_tiles_rate(fo, tall, info["nproc"])
+        value = all_pixels * args.steps / (tot_dev_ms * 1e-3) / 1e6
+        e2e = e2e_px / (e2e_ms * 1e-3) / 1e6 if e2e_ms else 0.0
+        line = {
+            "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": rig.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_name(args), "tiles_total": total, "tiles_rank0": count, "input_bytes_total": total * tile_px,
+                       "generator": "on device (felics_debug_generate_tiles), numpy twin felics_b200/synth.py checked on 3 tiles per rank",
+                       "l2": "not flushed: every rank's input (>= 2 GiB) and output exceed the 126 MB L2; each step timed with CUDA events on the launching stream",
+                       "fel_bytes_total": int(all_fel), "bits_per_sample": 8.0 * all_fel / max(all_pixels, 1),
+                       "sizes_gathered": int(len(all_sizes)), "gather": "sharding.gather_sizes over " + ("NCCL" if rig.world > 1 else "one process")},
+            "roofline": roof,
+            "cpu_baseline": {"value": allc, "unit": "MPixel/s", "cores": min(info["nproc"], nall), "kind": "port",
+                             "sample": f"first {nall} tiles of rank 0's shard, one image per thread at a time on all host threads",
+                             "single_thread": {"value": one, "unit": "MPixel/s", "cores": 1, "sample": f"first {n1} tiles of rank 0's shard"}, **info},
+            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": e2e_tiles * tile_px, "d2h_bytes_per_step": e2e_fel + 8 * (e2e_tiles + 1),
+                    "ms_per_step": e2e_ms, "tiles_per_rank": e2e_tiles, "rank0_mpixel_s": e2e_rate_local,
+                    "note": "felics_compress_batch on pinned host buffers; sub-batches copy in / encode / copy out on three streams"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": dec_bad == 0.0,
+                        "files": total, "note": "whole shard as one batch, one warp per file"} if decode else None),
+            "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
+            "parity": (None if not args.verify else (f"bit-exact vs oracle on {int(n_checked)} sampled tiles" if bad == 0 else f"MISMATCH vs oracle ({int(bad)} of {int(n_checked)})")),
+            "stream_redone": codec.stream_redone(),
+            "wall_s_timed_region": wall_dev,
+        }
+    del d_in, d_out, pin_in, pin_out
+    torch.cuda.empty_cache()
+    return line
+
+
+# ---- single-image configs -------------------------------------------------------------------------
+def single_input(workload, rank, fb):
+    if workload == "gray16":
+        return gnat16_image(W16, H16, seed=2 + rank)[None], fb.Header(fb.ColorType.Gray, fb.PixelDepth.Sixteen, W16, H16)
+    if workload == "rgb":
+        return gnat_rgb(W3, H3, rank=rank)[None], fb.Header(fb.ColorType.Rgb, fb.PixelDepth.Eight, W3, H3)
+    return gnat_image(W2, H2, seed=2 + rank)[None], fb.Header(fb.ColorType.Gray, fb.PixelDepth.Eight, W2, H2)
+
+
+def quick_single(workload, rig, steps=3):
+    """One of the single-image configs as an extra key of the default line: device-timed encode, oracle parity."""
+    torch, fb, codec = rig.torch, rig.fb, rig.codec
+    from oracle import felics_oracle as fo
+    host, hdr = single_input(workload, 0, fb)
+    pixels = host.size // (3 if workload == "rgb" else 1)
+    d_in = torch.from_numpy(host.view(np.uint8)).to(rig.dev)
+    cap = host.nbytes + host.nbytes // 2 + 4096
+    d_out = torch.empty(cap, dtype=torch.uint8, device=rig.dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=rig.dev)
+    fn = lambda: codec.compress_batch_device(1, d_in.data_ptr(), hdr, d_out.data_ptr(), cap)  # noqa: E731
+    for _ in range(3):
+        offsets = fn()
+    ms = rig.timed(fn, steps, flush)
+    fel = int(offsets[1])
+    ok = hashlib.sha256(d_out[:fel].cpu().numpy().tobytes()).digest() == hashlib.sha256(fo.compress(host[0])).digest()
+    return {"ms_per_step": sum(ms) / len(ms), "mpixel_s": pixels * len(ms) / (sum(ms) * 1e-3) / 1e6, "fel_bytes": fel,
+            "parity": "bit-exact vs oracle" if ok else "MISMATCH vs oracle", "l2": "flushed between timed steps"}
+
+
+def run_single(args, rig):
+    import ctypes as C
+    torch, fb, codec = rig.torch, rig.fb, rig.codec
+    rank, dev = rig.rank, rig.dev
+    host, hdr = single_input(args.workload, rank, fb)
+    n_img = 1
     samples = int(host.size)
     in_bytes = int(host.nbytes)                                # S * b of SURVEY.md 8(d)
     pixels = samples // (3 if args.workload == "rgb" else 1)   # an RGB pixel is one pixel, three samples
@@ -292,18 +542,8 @@ def run_ours(args):
     d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
     pin_out = torch.empty(cap, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    codec = felics_b200.Codec(device=local)
-    stream = torch.cuda.current_stream(dev)
-    codec.set_stream(stream.cuda_stream)
-    lib = felics_b200.load_library()
-    import ctypes as C
-    chdr = felics_b200._c_header(hdr)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    lib = rig.lib
+    chdr = fb._c_header(hdr)
 
     def encode_device():
         return codec.compress_batch_device(n_img, d_in.data_ptr(), hdr, d_out.data_ptr(), cap)
@@ -311,29 +551,10 @@ def run_ours(args):
     host_offsets = np.zeros(n_img + 1, dtype=np.uint64)
 
     def encode_host():
-        rc = lib.felics_compress_batch(codec._h, n_img, C.c_void_p(pin_in.data_ptr()), C.byref(chdr), C.c_void_p(pin_out.data_ptr()), cap,
-                                       host_offsets.ctypes.data_as(C.POINTER(C.c_uint64)))
-        if rc:
-            raise RuntimeError(f"felics_compress_batch failed: {rc} {lib.felics_last_error().decode()}")
-        return host_offsets
+        encode_host_call(rig, n_img, pin_in, chdr, pin_out, cap, host_offsets)
 
-    def timed(fn, steps):
-        """K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
-        ms = []
-        for _ in range(steps):
-            flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(dev)
-            a.record(stream)
-            fn()
-            b.record(stream)
-            torch.cuda.synchronize(dev)
-            ms.append(a.elapsed_time(b))
-        return ms
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(rig.local)
     sampler.start()   # nvidia-smi needs a moment to come up: start before the warm-up, count samples from the timed region on
-    # warm-up (also sizes the scratch buffers)
     for _ in range(max(args.warmup, 1)):
         offsets = encode_device()
     for _ in range(max(1, min(args.warmup, 2))):
@@ -341,53 +562,32 @@ def run_ours(args):
     fel_bytes = int(offsets[n_img])
 
     codec.profile(True)
-    barrier()
+    rig.barrier()
     sampler.mark()
     t_wall0 = time.perf_counter()
-    ms_dev = timed(encode_device, args.steps)
+    ms_dev = rig.timed(encode_device, args.steps, flush)
     wall_dev = time.perf_counter() - t_wall0
-    barrier()
+    rig.barrier()
     stages = codec.stage_times()
     launches = codec.total_launches()
     codec.profile(False)
-    barrier()
-    ms_e2e = timed(encode_host, args.steps)
-    barrier()
+    rig.barrier()
+    ms_e2e = rig.timed(encode_host, args.steps, flush)
+    rig.barrier()
     clocks = sampler.stop()
 
-    # decode (reported, not the target): the same .fel decoded on the GPU, timed once per step budget
+    # decode (reported, not the target): the same .fel decoded on the GPU, once
     d_pix_out = torch.empty(in_bytes, dtype=torch.uint8, device=dev)
-    dec_steps = 1 if args.workload != "tiles" else min(args.steps, 3)
     codec.profile(True)
     t0 = time.perf_counter()
     lossless = True
     if args.decode:
-        for _ in range(dec_steps):
-            status = codec.decompress_batch_device(n_img, d_out.data_ptr(), offsets, hdr, d_pix_out.data_ptr())
+        status = codec.decompress_batch_device(n_img, d_out.data_ptr(), offsets, hdr, d_pix_out.data_ptr())
         torch.cuda.synchronize(dev)
         lossless = bool((not status.any()) and torch.equal(d_pix_out, d_in.view(-1)))
     dec_wall = time.perf_counter() - t0
     dec_stage = codec.stage_times()
     codec.profile(False)
-
-    # a file is a serial bit chain: decode throughput comes from batches.  For the single-image workloads also report the
-    # same pixels cut into 512x512 tiles, encoded and decoded as one batch (rank 0 only, informational).
-    batch_decode = None
-    if args.decode and args.workload == "image" and rank == 0:
-        tiles = np.ascontiguousarray(host[0].reshape(H2 // TILE_H, TILE_H, W2 // TILE_W, TILE_W).swapaxes(1, 2).reshape(-1, TILE_H, TILE_W))
-        nt = tiles.shape[0]
-        thdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, TILE_W, TILE_H)
-        d_tiles = torch.from_numpy(tiles).to(dev)
-        d_out_t = torch.empty(cap, dtype=torch.uint8, device=dev)   # d_out still holds the timed output (parity is checked below)
-        toff = codec.compress_batch_device(nt, d_tiles.data_ptr(), thdr, d_out_t.data_ptr(), cap)
-        codec.profile(True)
-        tstatus = codec.decompress_batch_device(nt, d_out_t.data_ptr(), toff, thdr, d_pix_out.data_ptr())
-        torch.cuda.synchronize(dev)
-        tst = codec.stage_times()
-        codec.profile(False)
-        tms = tst["decode"][0] + tst["unplane"][0]
-        batch_decode = {"tiles": int(nt), "tile": f"{TILE_W}x{TILE_H}", "value": tiles.size / (tms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": tms,
-                        "lossless": bool((not tstatus.any()) and torch.equal(d_pix_out, d_tiles.view(-1)))}
 
     # opt-in band sidecar (NOT the reference format; include/felics_b200.h): the same .fel decoded band-parallel
     sidecar_decode = None
@@ -403,7 +603,7 @@ def run_ours(args):
         if rc == 0:
             fel_host = d_out[:fel_bytes].cpu().numpy()
             pix_host = np.empty(in_bytes, dtype=np.uint8)
-            ch2 = felics_b200._CHeader()
+            ch2 = fb._CHeader()
             codec.profile(True)
             t0 = time.perf_counter()
             rc = lib.felics_decompress_sidecar(codec._h, fel_host.ctypes.data, fel_host.size, side.ctypes.data, side.size, pix_host.ctypes.data,
@@ -417,105 +617,66 @@ def run_ours(args):
                               "lossless": bool(rc == 0 and np.array_equal(pix_host, host.view(np.uint8).reshape(-1))),
                               "note": "opt-in side file, not part of the reference .fel format"}
 
-    from felics_b200 import sharding
+    tot_dev_ms = rig.reduce(sum(ms_dev), "max")
+    tot_e2e_ms = rig.reduce(sum(ms_e2e), "max")
+    all_pixels = rig.reduce(float(pixels), "sum")
+    dec_ms = rig.reduce(dec_stage["decode"][0] + dec_stage["unplane"][0], "max")
+    ok_all = rig.reduce(0.0 if lossless else 1.0, "sum") == 0.0
 
-    def reduce_max(x):
-        return sharding.reduce_scalar(x, "max", device=dev)
+    if rank != 0:
+        return None
+    from oracle import felics_oracle as fo
+    enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane") and v[1]}
+    roof = roofline_of(enc_stages, args.steps, in_bytes + fel_bytes, sum(ms_dev), args.workload)
+    # CPU baseline: the oracle on the whole image, one thread (a single image is serial in the reference)
+    t0 = time.perf_counter()
+    want = fo.compress(host[0])
+    cpu_s = time.perf_counter() - t0
+    parity = None
+    if args.verify:
+        got = d_out[:fel_bytes].cpu().numpy().tobytes()
+        parity = "bit-exact vs oracle" if hashlib.sha256(got).digest() == hashlib.sha256(want).digest() else "MISMATCH vs oracle"
+    value = all_pixels * args.steps / (tot_dev_ms * 1e-3) / 1e6
+    e2e = all_pixels * args.steps / (tot_e2e_ms * 1e-3) / 1e6
+    return {
+        "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": rig.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "l2": "flushed between timed steps (256 MiB device write); each step timed with CUDA events on the launching stream",
+                   "fel_bytes_rank0": fel_bytes, "bits_per_sample": 8.0 * fel_bytes / samples, "msample_per_s": value * samples / pixels},
+        "roofline": roof,
+        "cpu_baseline": {"value": pixels / cpu_s / 1e6, "unit": "MPixel/s", "cores": 1, "kind": "port",
+                         "sample": "the whole image of rank 0, one thread (a single image is serial in the reference)", **cpu_info()},
+        "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
+                "ms_per_step": tot_e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": ok_all,
+                    "wall_ms": 1e3 * dec_wall, "with_sidecar": sidecar_decode} if args.decode else None),
+        "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
+        "parity": parity,
+        "wall_s_timed_region": wall_dev,
+    }
 
-    def reduce_sum(x):
-        return sharding.reduce_scalar(x, "sum", device=dev)
 
-    tot_dev_ms = reduce_max(sum(ms_dev))
-    tot_e2e_ms = reduce_max(sum(ms_e2e))
-    all_pixels = reduce_sum(float(pixels))
-    dec_ms = reduce_max(dec_stage["decode"][0] + dec_stage["unplane"][0]) / dec_steps
-    ok_all = reduce_sum(0.0 if lossless else 1.0) == 0.0
-
-    if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        # dominant kernel = the stage with the largest device time
-        enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane")}
-        dom = max(enc_stages, key=lambda k: enc_stages[k][0])
-        dom_ms, dom_launches = enc_stages[dom]
-        alg_bytes = in_bytes + fel_bytes        # S*b + C, per launch: one launch covers the whole batch
-        dom_avg_ms = dom_ms / max(dom_launches, 1)
-        launches_per_step = max(dom_launches / max(args.steps, 1), 1.0)   # batches larger than the scratch budget run in several sub-batches
-        alg_bytes_per_launch = alg_bytes / launches_per_step
-        achieved = alg_bytes_per_launch / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
-        whole_achieved = alg_bytes * args.steps / (sum(ms_dev) * 1e-3) / 1e9
-
-        # CPU baseline: the oracle on a bounded sample of this workload, rank 0 only
-        from oracle import felics_oracle as fo
-        if args.workload == "tiles":
-            sample_imgs = host[:64]
-            t0 = time.perf_counter()
-            fo.compress_many(sample_imgs, 0, 0, TILE_W, TILE_H)
-            cpu_s = time.perf_counter() - t0
-            cpu_px = int(sample_imgs.size)
-            sample = "first 64 tiles of rank 0's batch, 1 thread"
-            want = fo.compress(host[0])
-            got = d_out[: int(offsets[1])].cpu().numpy().tobytes()
-        elif args.workload == "gray16":
-            rows = 2048
-            t0 = time.perf_counter()
-            fo.compress(host[0][:rows])
-            cpu_s = time.perf_counter() - t0
-            cpu_px = W16 * rows
-            sample = f"top {rows} rows of rank 0's image (4096x{rows} gray16), 1 thread (a single image is serial in the reference)"
-            want = None
-            got = d_out[:fel_bytes].cpu().numpy().tobytes()
-        elif args.workload == "rgb":
-            rows = 1024
-            t0 = time.perf_counter()
-            fo.compress(host[0][:rows])
-            cpu_s = time.perf_counter() - t0
-            cpu_px = W3 * rows
-            sample = f"top {rows} rows of rank 0's frame (7680x{rows} RGB), 1 thread (a single image is serial in the reference)"
-            want = None
-            got = d_out[:fel_bytes].cpu().numpy().tobytes()
-        else:
-            rows = 2048
-            t0 = time.perf_counter()
-            fo.compress(host[0][:rows])
-            cpu_s = time.perf_counter() - t0
-            cpu_px = W2 * rows
-            sample = f"top {rows} rows of rank 0's image (8192x{rows}), 1 thread (a single image is serial in the reference)"
-            want = None
-            got = d_out[:fel_bytes].cpu().numpy().tobytes()
-        parity = None
-        if args.verify:
-            if want is None:
-                want = fo.compress(host[0])
-            parity = "bit-exact vs oracle" if hashlib.sha256(got).digest() == hashlib.sha256(want).digest() else "MISMATCH vs oracle"
-
-        value = all_pixels * args.steps / (tot_dev_ms * 1e-3) / 1e6
-        e2e = all_pixels * args.steps / (tot_e2e_ms * 1e-3) / 1e6
-        line = {
-            "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
-            "config": {"workload": workload_name(args), "l2": "flushed between timed steps (256 MiB device write); each step timed with CUDA events on the launching stream",
-                       "fel_bytes_rank0": fel_bytes, "bits_per_sample": 8.0 * fel_bytes / samples,
-                       "msample_per_s": value * samples / pixels},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(dom) if args.workload == "image" else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "kernel_ms_per_launch": dom_avg_ms, "kernel_launches_per_step": launches_per_step,
-                         "whole_encode_achieved_gbs": whole_achieved, "whole_encode_frac": whole_achieved / peak},
-            "cpu_baseline": {"value": cpu_px / cpu_s / 1e6, "unit": "MPixel/s", "cores": 1, "kind": "port", "sample": sample},
-            "e2e": {"value": e2e, "unit": "MPixel/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": fel_bytes + 8 * (n_img + 1),
-                    "ms_per_step": tot_e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": ok_all,
-                        "wall_ms": 1e3 * dec_wall / dec_steps, "as_batch_of_tiles": batch_decode, "with_sidecar": sidecar_decode} if args.decode else None),
-            "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
-            "parity": parity,
-            "wall_s_timed_region": wall_dev,
-        }
+def run_ours(args):
+    rig = Rig()
+    if args.workload == "tiles":
+        line = run_tiles(args, rig)
+        if line is not None and args.extras and rig.world == 1:
+            # the single-image configs as extra keys (one B200, informational; `--workload image|rgb|gray16` gives their full lines)
+            extra = {}
+            for wl, key in (("image", "configs[1] 8192x8192 gray8"), ("rgb", "configs[2] 7680x4320 RGB8"), ("gray16", "4096x4096 gray16")):
+                try:
+                    extra[key] = quick_single(wl, rig)
+                except Exception as exc:   # informational only: never lose the main line
+                    extra[key] = {"error": str(exc)}
+            line["other_configs"] = extra
+    else:
+        line = run_single(args, rig)
+    if line is not None:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    rig.finish()
 
 
 def main():
@@ -524,10 +685,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["image", "rgb", "tiles", "gray16"], default="image")
-    ap.add_argument("--tiles", type=int, default=2048, help="tiles per GPU for --workload tiles")
+    ap.add_argument("--workload", choices=["tiles", "image", "rgb", "gray16"], default="tiles")
+    ap.add_argument("--tiles", type=int, default=TOTAL_TILES, help="tiles in the whole batch (sharded over the GPUs) for --workload tiles")
+    ap.add_argument("--parity-tiles", type=int, default=256, help="tiles per rank compared with the oracle")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check of the timed output")
-    ap.add_argument("--no-decode", dest="decode", action="store_false", help="skip the (slow, single-stream) decode measurement")
+    ap.add_argument("--no-decode", dest="decode", action="store_false", help="skip the decode measurement")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="skip the single-image configs reported beside the tile batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

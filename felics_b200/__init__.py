@@ -119,8 +119,12 @@ def load_library() -> C.CDLL:
     L.felics_profile_stage_launches.restype = C.c_uint64
     L.felics_profile_total_launches.argtypes = [vp]
     L.felics_profile_total_launches.restype = C.c_uint64
+    # test / bench aids (include/felics_b200_debug.h)
     L.felics_debug_last_records.argtypes = [vp, vp, sz]
     L.felics_debug_counters.argtypes = [vp, vp]
+    L.felics_debug_stream_redone.argtypes = [vp]
+    L.felics_debug_stream_redone.restype = C.c_uint64
+    L.felics_debug_generate_tiles.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64]
     _lib = L
     return L
 
@@ -361,6 +365,16 @@ class Codec:
         out = np.zeros(8, dtype=np.uint32)
         self._lib.felics_debug_counters(self._h, out.ctypes.data)
         return out
+
+    def stream_redone(self) -> int:
+        """Images the streaming band encoder handed to the general pipeline (streams above 10 bits per pixel)."""
+        return int(self._lib.felics_debug_stream_redone(self._h))
+
+    def generate_tiles(self, d_out: int, first_tile: int, n_tiles: int, seed: int = 1):
+        """configs[3] tiles generated on the device (felics_b200_debug.h); numpy twin: felics_b200.synth.tile_batch."""
+        rc = self._lib.felics_debug_generate_tiles(self._h, C.c_void_p(d_out), first_tile, n_tiles, seed)
+        if rc:
+            _raise(rc)
 
     def debug_last_records(self, count: int) -> np.ndarray:
         out = np.zeros(count, dtype=np.uint32)

@@ -1,6 +1,7 @@
 // C ABI of the B200 FELICS engine (include/felics_b200.h): contexts, container header,
 // host-memory entry points (staging copies around the device pipeline), profiling.
 #include "ctx.h"
+#include "../../include/felics_b200_debug.h"
 
 #include <cstdarg>
 #include <cstdio>
@@ -79,7 +80,7 @@ int profile_collect(felics_ctx *ctx) {
 }
 
 static const char *kStageNames[ST_COUNT] = {"planes", "hist", "chainscan", "tilebase", "scatter", "prefix", "grpscan",
-                                            "spec", "walk", "kfill", "code", "bitscan", "pack", "decode", "unplane"};
+                                            "spec", "walk", "kfill", "code", "bitscan", "pack", "decode", "unplane", "stream", "compact"};
 
 static int check_header(const felics_header *hdr) {
     if (!hdr) { set_error("null header"); return FELICS_ERR_INVALID_ARGUMENT; }
@@ -130,6 +131,10 @@ int felics_ctx_create(int device, felics_ctx **out) {
         ctx->no_overlap = no && no[0] == '1';
         const char *nh = getenv("FELICS_B200_NO_HOP");       // debug switch: no segment hops
         ctx->no_hop = nh && nh[0] == '1';
+        const char *nst = getenv("FELICS_B200_NO_STREAM");   // debug/bench switch: gray batches through the multi-kernel pipeline
+        ctx->no_stream = nst && nst[0] == '1';
+        const char *smin = getenv("FELICS_B200_STREAM_MIN");
+        if (smin) ctx->stream_min = (size_t)strtoull(smin, nullptr, 0);
     }
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ctx; return FELICS_ERR_CUDA; }
@@ -154,6 +159,7 @@ void felics_ctx_destroy(felics_ctx *ctx) {
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
         if (ctx->ev_pack[i]) cudaEventDestroy(ctx->ev_pack[i]);
         if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+        if (ctx->ev_sizes[i]) cudaEventDestroy(ctx->ev_sizes[i]);
         if (ctx->stage_in[i]) cudaFree(ctx->stage_in[i]);
         if (ctx->stage_out[i]) cudaFree(ctx->stage_out[i]);
     }
@@ -243,6 +249,8 @@ int felics_compress_batch(felics_ctx *ctx, size_t n, const void *pixels, const f
     if (n == 0) return FELICS_OK;
     size_t in_bytes = felics_pixel_bytes(hdr) * n;
     if (in_bytes && !pixels) { set_error("null pixels"); return FELICS_ERR_INVALID_ARGUMENT; }
+    // batches of gray images: one block per image (stream.cu), sub-batches double buffered over three streams
+    if (stream_eligible(ctx, n, nullptr, *hdr)) return stream_encode_batch_host(ctx, n, pixels, *hdr, arena, arena_cap, offsets);
     // 8-bit samples: sub-batches stream through the device (copy in / encode / copy out overlap)
     // (images without pixels: any non-null host pointer selects the streaming path, nothing is read through it)
     if (hdr->pixel_depth == 0) return encode_batch_device(ctx, n, nullptr, *hdr, nullptr, arena, arena_cap, offsets, pixels ? pixels : (const void *)arena);

@@ -27,6 +27,8 @@ enum Stage : int {
     ST_PACK,         // MSB-first bit packing
     ST_DECODE,       // bit-serial decode, one stream per warp
     ST_UNPLANE,      // i16 planes -> pixels (+ inverse YCoCg-R), range checks
+    ST_STREAM,       // streaming band encoder: one block per image, everything between pixels and bits on chip (stream.cu)
+    ST_COMPACT,      // image offsets + copy of the finished streams to their place in the arena
     ST_COUNT
 };
 
@@ -64,6 +66,7 @@ struct felics_ctx {
     size_t staging_out_cap = 0;
     // host-memory batches: sub-batches are copied in, encoded and copied out on three streams (double buffered)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_sizes[2] = {nullptr, nullptr};
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_pack[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void *stage_in[2] = {nullptr, nullptr};
     size_t stage_in_cap[2] = {0, 0};
@@ -89,6 +92,11 @@ struct felics_ctx {
     unsigned walk_per_sm = 1;     // walker blocks per SM while the speculative kernels run beside them
     bool no_quads = false;        // debug switch: one sample per thread in the histogram / code kernels
     bool serial16 = false;        // debug switch: the one-warp-per-image 16-bit encoder instead of the parallel one
+    bool no_stream = false;       // debug/bench switch: batches of gray images through the multi-kernel pipeline instead of stream.cu
+    size_t stream_min = 96;       // smallest batch the streaming band encoder takes (one block per image: fewer leave SMs idle)
+    bool stream_attr_done = false;
+    int sm_count = 148;
+    uint64_t stream_redone = 0;   // images re-encoded by the general pipeline because their stream overflowed its slot
     std::vector<felics::ProfEntry> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     double stage_ms[felics::ST_COUNT] = {0};
@@ -131,6 +139,12 @@ int profile_collect(felics_ctx *ctx);  // after a stream sync: fold pending even
 // encode.cu
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                         uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels = nullptr);
+// stream.cu: batches of 8-bit gray images, one block per image
+bool stream_eligible(const felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr);
+int stream_encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena, size_t arena_cap,
+                               uint64_t *offsets_host);
+int stream_encode_batch_host(felics_ctx *ctx, size_t n, const void *h_pixels, const felics_header &hdr, uint8_t *h_arena, size_t arena_cap,
+                             uint64_t *offsets_host);
 // encode16.cu: 16-bit samples
 int encode16_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr,
                           uint8_t *d_arena, uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host);

@@ -1362,6 +1362,8 @@ namespace felics {
 int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header &hdr, uint8_t *d_arena,
                         uint8_t *h_arena, size_t arena_cap, uint64_t *offsets_host, const void *h_pixels) {
     ctx->last.valid = false;
+    // batches of gray images, device resident: one block per image, everything on chip (stream.cu); any arena alignment
+    if (d_arena && !h_pixels && stream_eligible(ctx, n, d_pixels, hdr)) return stream_encode_batch_device(ctx, n, d_pixels, hdr, d_arena, arena_cap, offsets_host);
     if (d_arena && ((uintptr_t)d_arena & 3) != 0) {
         set_error("device arena must be 4-byte aligned");
         return FELICS_ERR_INVALID_ARGUMENT;
