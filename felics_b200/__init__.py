@@ -311,7 +311,7 @@ class Codec:
         ch = _c_header(header)
         rc = self._lib.felics_decompress_batch(self._h, n, arena.ctypes.data, offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                C.byref(ch), out.ctypes.data, status.ctypes.data_as(C.POINTER(C.c_int)))
-        if rc and rc in (-9, -10, -12):
+        if rc and (rc in (-9, -10, -12) or rc not in status[:n]):   # a failure of the whole call, not of one image
             _raise(rc)
         return out, status[:n]
 
@@ -336,7 +336,7 @@ class Codec:
         ch = _c_header(header)
         rc = self._lib.felics_decompress_batch_device(self._h, n, C.c_void_p(d_arena), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                       C.byref(ch), C.c_void_p(d_pixels_out), status.ctypes.data_as(C.POINTER(C.c_int)))
-        if rc and rc in (-9, -10, -12):
+        if rc and (rc in (-9, -10, -12) or rc not in status[:n]):   # a failure of the whole call, not of one image
             _raise(rc)
         return status[:n]
 

@@ -133,6 +133,8 @@ int felics_ctx_create(int device, felics_ctx **out) {
         ctx->no_hop = nh && nh[0] == '1';
         const char *nst = getenv("FELICS_B200_NO_STREAM");   // debug/bench switch: gray batches through the multi-kernel pipeline
         ctx->no_stream = nst && nst[0] == '1';
+        const char *sdbg = getenv("FELICS_B200_STREAM_DBG");
+        if (sdbg) ctx->stream_dbg = (uint32_t)strtoul(sdbg, nullptr, 0);
         const char *smin = getenv("FELICS_B200_STREAM_MIN");
         if (smin) ctx->stream_min = (size_t)strtoull(smin, nullptr, 0);
     }
@@ -153,6 +155,7 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->staging_in) cudaFree(ctx->staging_in);
     if (ctx->staging_out) cudaFree(ctx->staging_out);
     if (ctx->tables16) cudaFree(ctx->tables16);
+    if (ctx->exact_buf) cudaFree(ctx->exact_buf);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -283,6 +286,7 @@ int felics_decompress_batch(felics_ctx *ctx, size_t n, const uint8_t *arena, con
     if (rc) return rc;
     if ((rc = bind_device(ctx))) return rc;
     if (n == 0) return FELICS_OK;
+    if ((rc = check_offsets(n, offsets))) return rc;   // before offsets[n] bytes are taken to be the whole arena
     size_t in_bytes = (size_t)offsets[n];
     size_t out_bytes = felics_pixel_bytes(hdr) * n;
     if ((rc = ensure_buffer(ctx, &ctx->staging_in, &ctx->staging_in_cap, in_bytes + 16))) return rc;

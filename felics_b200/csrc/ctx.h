@@ -72,6 +72,8 @@ struct felics_ctx {
     size_t stage_in_cap[2] = {0, 0};
     void *stage_out[2] = {nullptr, nullptr};
     size_t stage_out_cap[2] = {0, 0};
+    void *exact_buf = nullptr;    // i32 planes of one image: files the fast decoders hand to k_decode_exact
+    size_t exact_cap = 0;
     void *pinned = nullptr;       // small pinned host buffer for read-backs
     size_t pinned_cap = 0;
 
@@ -95,6 +97,7 @@ struct felics_ctx {
     bool no_stream = false;       // debug/bench switch: batches of gray images through the multi-kernel pipeline instead of stream.cu
     size_t stream_min = 96;       // smallest batch the streaming band encoder takes (one block per image: fewer leave SMs idle)
     bool stream_attr_done = false;
+    uint32_t stream_dbg = 0;      // timing experiments (wrong output): see StreamArgs::dbg
     int sm_count = 148;
     uint64_t stream_redone = 0;   // images re-encoded by the general pipeline because their stream overflowed its slot
     std::vector<felics::ProfEntry> prof_pending;
@@ -157,6 +160,7 @@ int sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *h_out, size_t ca
 int decode_sidecar(felics_ctx *ctx, const uint8_t *h_fel, size_t len, const uint8_t *h_side, size_t side_len, void *h_pixels_out, size_t cap,
                    felics_header *hdr_out);
 // decode.cu
+int check_offsets(size_t n, const uint64_t *offsets);
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
                         const felics_header &hdr, void *d_pixels_out, int *status_host);
 

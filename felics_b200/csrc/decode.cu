@@ -74,6 +74,118 @@ struct BitReader {
     }
 };
 
+// Internal status of the fast decoders: the stream did something no valid file does (a sample outside the 16-bit planes,
+// a unary run of tens of thousands of ones).  The reference keeps such values as i32 and goes on, and what it finally reports
+// depends on what comes next (IoError at the end of the input, the `context <= max_context` assertion, InvalidValue at the
+// final try_into, compression.rs:208-243, :305-310), so the file is decoded again by k_decode_exact, which keeps i32 planes
+// and follows the reference check by check.  Never returned to the caller.
+constexpr int FELICS_NEED_EXACT = 1;
+
+struct ExactArgs {
+    const uint32_t *words;
+    uint64_t arena_words, off0, off1;
+    int32_t *planes;           // [nch][npix]
+    int *status;
+    uint32_t w, h, npix, nch;
+};
+
+// decompress_channel as written (compression.rs:151-248), one lane, i32 samples: only for files the fast decoders gave up on
+__global__ void __launch_bounds__(32) k_decode_exact(ExactArgs a) {
+    __shared__ uint32_t tab[(NBIN - 1) * NK];
+    const uint32_t lane = threadIdx.x;
+    int st = FELICS_OK;
+    BitReader br;
+    br.init(a.words, a.arena_words, 8 * (a.off0 + FELICS_HEADER_BYTES), 8 * a.off1);
+    const uint32_t w = a.w;
+    for (uint32_t ch = 0; ch < a.nch && st == FELICS_OK; ch++) {
+        for (uint32_t j = lane; j < (NBIN - 1) * NK; j += 32) tab[j] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            int32_t *pl = a.planes + (size_t)ch * a.npix;
+            const int32_t p1 = (int32_t)br.read(32), p2 = (int32_t)br.read(32);   // :161-162
+            if (br.eof) st = FELICS_ERR_IO;
+            else {
+                if (a.npix >= 1) pl[0] = p1;
+                if (a.npix >= 2) pl[1] = p2;
+            }
+            uint32_t x = 0, y = 0;
+            if (a.npix >= 3) { x = 2 % w; y = 2 / w; }
+            for (uint32_t i = 2; i < a.npix && st == FELICS_OK; i++) {
+                uint32_t ia, ib;
+                if (x > 0 && y > 0) { ia = i - 1; ib = i - w; }
+                else if (y == 0) { ia = i - 1; ib = i - 2; }
+                else if (y >= 2) { ia = i - w; ib = i - 2 * w; }
+                else { ia = i - w; ib = i - w + 1; }
+                const long long v1 = pl[ia], v2 = pl[ib];
+                const long long hi = max(v1, v2), lo = min(v1, v2);
+                if (hi - lo > 510ll) { st = FELICS_ERR_CORRUPT; break; }   // h - l overflow / assert!(context <= max_context), parameter_selection.rs:72
+                const uint32_t ctx = (uint32_t)(hi - lo);
+                uint32_t *row = tab + ctx * NK;
+                uint32_t rr[NK];
+#pragma unroll
+                for (int k = 0; k < NK; k++) rr[k] = row[k];
+                const int k = argmin_last(rr);                                // get_k before the marker is read (:202)
+                long long value;
+                const uint32_t in_range = br.read(1);                         // decode_intensity (:48-61)
+                uint32_t above = 0;
+                if (!in_range) above = br.read(1);
+                if (br.eof) { st = FELICS_ERR_IO; break; }
+                if (in_range) {
+                    const uint32_t nn = ctx + 1;
+                    const int m = 31 - __clz(nn);
+                    const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                    uint32_t xx = br.read((uint32_t)m);
+                    if (!br.eof && xx >= right_p) xx = (xx - right_p) * 2 + right_p + br.read(1);   // phase_in_coding.rs:102-109
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    xx = (xx + left_p) % nn;                                  // rotate_left (:55-57)
+                    value = lo + (long long)xx;
+                } else {
+                    const uint32_t q = br.read_unary0();
+                    const uint32_t rem = br.eof ? 0u : br.read((uint32_t)k);
+                    if (br.eof) { st = FELICS_ERR_IO; break; }
+                    if (((unsigned long long)q << k) > 0xFFFFFFFFull) { st = FELICS_ERR_CORRUPT; break; }   // checked_mul(..).unwrap(), rice_coding.rs:50
+                    const uint32_t e = (q << k) + rem;
+                    uint32_t mn = 0xffffffffu;
+#pragma unroll
+                    for (int kk = 0; kk < NK; kk++) {                         // update (parameter_selection.rs:49-65)
+                        rr[kk] += (e >> kk) + 1u + (uint32_t)kk;
+                        mn = min(mn, rr[kk]);
+                    }
+                    if (mn > HALVE_AT) {
+#pragma unroll
+                        for (int kk = 0; kk < NK; kk++) rr[kk] >>= 1;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < NK; kk++) row[kk] = rr[kk];
+                    if (e > 0x7FFFFFFFu) { st = FELICS_ERR_INVALID_VALUE; break; }   // u32 -> i32 try_into (:222-224, :234-236)
+                    value = above ? hi + (long long)e + 1 : lo - (long long)e - 1;
+                }
+                if (value < -2147483648ll || value > 2147483647ll) { st = FELICS_ERR_VALUE_OVERFLOW; break; }   // checked_add / checked_sub
+                pl[i] = (int32_t)value;
+                if (++x == w) { x = 0; y++; }
+            }
+        }
+        st = __shfl_sync(0xffffffffu, st, 0);
+    }
+    if (lane == 0) *a.status = st;
+}
+
+// i32 planes of one image -> pixels with the try_into range checks (compression.rs:305-310, :402-407; color_transform.rs:20-26)
+__global__ void k_unplane_exact8(const int32_t *__restrict__ planes, uint8_t *__restrict__ px, uint32_t npix, uint32_t nch, int *__restrict__ status) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        if (nch == 1) {
+            const int v = planes[i];
+            if (v < 0 || v > 255) { atomicCAS(status, FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
+            px[i] = (uint8_t)v;
+        } else {
+            const long long y = planes[i], co = planes[(size_t)npix + i], cg = planes[2 * (size_t)npix + i];
+            const long long t = y - cg / 2, g = cg + t, b = t - co / 2, r = b + co;
+            if (r < 0 || r > 255 || g < 0 || g > 255 || b < 0 || b > 255) { atomicCAS(status, FELICS_OK, FELICS_ERR_INVALID_VALUE); continue; }
+            px[3 * i] = (uint8_t)r; px[3 * i + 1] = (uint8_t)g; px[3 * i + 2] = (uint8_t)b;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
     __shared__ uint32_t tab[(NBIN - 1) * NK];
     const uint32_t img = blockIdx.x;
@@ -117,7 +229,7 @@ __global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
             int32_t p2 = (int32_t)br.read(32);
             if (br.eof) st = FELICS_ERR_IO;
             else if (a.npix >= 1) {
-                if (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767))) st = FELICS_ERR_INVALID_VALUE;
+                if (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767))) st = FELICS_NEED_EXACT;
                 else {
                     pl[0] = (int16_t)p1;
                     if (a.npix >= 2) pl[1] = (int16_t)p2;
@@ -159,7 +271,7 @@ __global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
                     uint32_t q = br.read_unary0();
                     uint32_t rem = br.read((uint32_t)k);
                     if (br.eof) { st = FELICS_ERR_IO; break; }
-                    if (q > 70000u) { st = FELICS_ERR_INVALID_VALUE; break; }
+                    if (q > 70000u) { st = FELICS_NEED_EXACT; break; }
                     uint32_t e = (q << k) + rem;
                     uint32_t mn = 0xffffffffu;
 #pragma unroll
@@ -175,7 +287,7 @@ __global__ void __launch_bounds__(32) k_decode_wide(DecArgs a, uint32_t n) {
                     for (int kk = 0; kk < NK; kk++) row[kk] = rr[kk];
                     value = above ? hi + (int)e + 1 : lo - (int)e - 1;    // (:216-243)
                 }
-                if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
+                if (value < -32768 || value > 32767) { st = FELICS_NEED_EXACT; break; }
                 pl[i] = (int16_t)value;
                 if (++x == w) { x = 0; y++; }
             }
@@ -301,7 +413,7 @@ __device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t
                     }
                     const uint32_t rem = br.read(k);
                     if (br.eof()) { st = FELICS_ERR_IO; break; }
-                    if (q > 70000u) { st = FELICS_ERR_INVALID_VALUE; break; }
+                    if (q > 70000u) { st = FELICS_NEED_EXACT; break; }
                     const uint32_t e = (q << k) + rem;
                     uint32_t mn = 0xffffffffu;
 #pragma unroll
@@ -318,7 +430,7 @@ __device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t
                     *reinterpret_cast<uint2 *>(row + 4) = make_uint2(rr[4], rr[5]);
                     value = above ? hi + (int)e + 1 : lo - (int)e - 1;  // (:216-243)
                 }
-                if (value < -32768 || value > 32767) { st = FELICS_ERR_INVALID_VALUE; break; }
+                if (value < -32768 || value > 32767) { st = FELICS_NEED_EXACT; break; }
                 cur[x] = (int16_t)value;
                 left = value;
             }
@@ -382,7 +494,7 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
             p1 = (int32_t)br.read(32);   // read_signed(32) twice (:161-162)
             p2 = (int32_t)br.read(32);
             if (br.eof()) st = FELICS_ERR_IO;
-            else if (a.npix >= 1 && (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767)))) st = FELICS_ERR_INVALID_VALUE;
+            else if (a.npix >= 1 && (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767)))) st = FELICS_NEED_EXACT;
         }
         st = __shfl_sync(0xffffffffu, st, 0);
         if (st != FELICS_OK || a.npix == 0) continue;
@@ -541,10 +653,11 @@ __global__ void __launch_bounds__(32) k16_decode(Dec16Args a, uint32_t n) {
                         const uint32_t q = br.read_unary0();
                         const uint32_t rem = br.read((uint32_t)k);
                         if (br.eof) { st = FELICS_ERR_IO; break; }
-                        if (q > (1u << 20)) { st = FELICS_ERR_INVALID_VALUE; break; }
+                        if (((unsigned long long)q << k) > 0xFFFFFFFFull) { st = FELICS_ERR_CORRUPT; break; }   // checked_mul(..).unwrap(), rice_coding.rs:50
                         const uint32_t e = (q << k) + rem;
                         update16(cnt, e);
                         est.store(ctx, cnt);
+                        if (e > 0x7FFFFFFFu) { st = FELICS_ERR_INVALID_VALUE; break; }   // u32 -> i32 try_into (compression.rs:222-224, :234-236)
                         value = above ? hi + (long long)e + 1 : lo - (long long)e - 1;   // (:216-243)
                     }
                     if (value < -2147483648ll || value > 2147483647ll) { st = FELICS_ERR_VALUE_OVERFLOW; break; }   // checked_add / checked_sub
@@ -706,7 +819,7 @@ __global__ void __launch_bounds__(32) k_decode_bands(BandArgs a) {
             p1 = (int32_t)br.read(32);   // read_signed(32) twice (compression.rs:161-162)
             p2 = (int32_t)br.read(32);
             if (br.eof()) st = FELICS_ERR_IO;
-            else if (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767))) st = FELICS_ERR_INVALID_VALUE;
+            else if (p1 < -32768 || p1 > 32767 || (a.npix >= 2 && (p2 < -32768 || p2 > 32767))) st = FELICS_NEED_EXACT;
         }
     }
     st = __shfl_sync(0xffffffffu, st, 0);
@@ -736,7 +849,7 @@ int decode_sidecar(felics_ctx *ctx, const uint8_t *h_fel, size_t len, const uint
     memcpy(sh, h_side, sizeof(sh));
     const size_t entry = sidecar_entry_bytes(hdr.width);
     const uint32_t band_rows = sh[5], nbands = sh[6];
-    if (sh[0] != SIDECAR_MAGIC || sh[1] != 1u || sh[2] != hdr.width || sh[3] != hdr.height || sh[4] != nch || band_rows < 2 ||
+    if (sh[0] != SIDECAR_MAGIC || sh[1] != SIDECAR_VERSION || sh[2] != hdr.width || sh[3] != hdr.height || sh[4] != nch || band_rows < 2 ||
         band_rows % sidecar_row_unit(hdr.width ? hdr.width : 1) != 0 || nbands != std::max<uint32_t>(1, (hdr.height + band_rows - 1) / band_rows) ||
         sh[7] != (uint32_t)entry || side_len != SIDECAR_HEADER_BYTES + (size_t)nch * nbands * entry) {
         set_error("sidecar header does not match the file");
@@ -788,7 +901,22 @@ int decode_sidecar(felics_ctx *ctx, const uint8_t *h_fel, size_t len, const uint
     FELICS_CUDA_TRY(cudaStreamSynchronize(st));
     FELICS_CUDA_TRY(cudaGetLastError());
     if ((rc = profile_collect(ctx))) return rc;
+    if (status == FELICS_NEED_EXACT) {   // a band left the 16-bit planes: the plain decoder settles what the reference would report
+        uint64_t off[2] = {0, (uint64_t)len};
+        int st1 = 0;
+        return felics_decompress_batch(ctx, 1, h_fel, off, &hdr, h_pixels_out, &st1);
+    }
     return status;
+}
+
+// offsets[i] <= offsets[i + 1] for every image: the kernels take lengths as differences and read headers at offsets[i]
+int check_offsets(size_t n, const uint64_t *offsets) {
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i] > offsets[i + 1]) {
+            set_error("offsets must not decrease (offsets[%zu] = %llu > offsets[%zu] = %llu)", i, (unsigned long long)offsets[i], i + 1, (unsigned long long)offsets[i + 1]);
+            return FELICS_ERR_INVALID_ARGUMENT;
+        }
+    return FELICS_OK;
 }
 
 int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets_host,
@@ -801,6 +929,7 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     uint64_t npix64 = (uint64_t)hdr.width * hdr.height;
     if (npix64 > 0xffffffffull) return FELICS_ERR_INVALID_DIMENSIONS;   // checked_mul, compression.rs:176-180
     if (npix64 > 0x7fff0000ull) { set_error("image too large for one call"); return FELICS_ERR_INVALID_DIMENSIONS; }
+    if (int orc = check_offsets(n, offsets_host)) return orc;
     if (hdr.pixel_depth != 0) return decode16_batch_device(ctx, n, d_arena, offsets_host, hdr, d_pixels_out, status_host);
     cudaStream_t st = ctx->stream;
     const uint32_t npix = (uint32_t)npix64;
@@ -851,6 +980,21 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     FELICS_CUDA_TRY(cudaGetLastError());
     rc = profile_collect(ctx);
     if (rc) return rc;
+    // files the fast decoder gave up on: again, the reference's way (i32 samples), one at a time
+    for (size_t i = 0; i < n; i++) {
+        if (status_host[i] != FELICS_NEED_EXACT) continue;
+        const size_t pl_bytes = align_up((size_t)nch * npix * sizeof(int32_t) + 16, 256);
+        if ((rc = ensure_buffer(ctx, &ctx->exact_buf, &ctx->exact_cap, pl_bytes + 256))) return rc;
+        ExactArgs ea;
+        ea.words = (const uint32_t *)d_arena; ea.arena_words = a.arena_words; ea.off0 = offsets_host[i]; ea.off1 = offsets_host[i + 1];
+        ea.planes = (int32_t *)ctx->exact_buf; ea.status = (int *)((uint8_t *)ctx->exact_buf + pl_bytes);
+        ea.w = hdr.width; ea.h = hdr.height; ea.npix = npix; ea.nch = nch;
+        k_decode_exact<<<1, 32, 0, st>>>(ea);
+        if (npix > 0) k_unplane_exact8<<<(unsigned)std::min<size_t>(((size_t)npix + 255) / 256, 148 * 8), 256, 0, st>>>(
+            ea.planes, (uint8_t *)d_pixels_out + i * (size_t)npix * nch, npix, nch, ea.status);
+        FELICS_CUDA_TRY(cudaMemcpyAsync(&status_host[i], ea.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     for (size_t i = 0; i < n; i++)
         if (status_host[i] != FELICS_OK) return status_host[i];
     return FELICS_OK;

@@ -4,8 +4,9 @@
 // (parameter_selection.rs:24-33, all 511 x 6 counts as they stand before the band's first pixel), the row above and the
 // first sample of the row above that (misc.rs:6-24).  Bands then decode side by side.  The .fel bytes are untouched.
 //
-// Layout (little endian):  header 32 B {"FLSC", version 1, width, height, channels, band_rows, bands per plane, entry bytes}
-//                          entries, plane-major: {u64 bit position in the file, i32 col0_b, u32 0, u32 table[511 * 6], i16 row[width]}
+// Layout (little endian):  header 32 B {"FLSC", version 2, width, height, channels, band_rows, bands per plane, entry bytes}
+//                          entries, plane-major: {u64 bit position in the file, i32 col0_b, u32 0, u32 table[511 * 6], i16 row[width], padded to 8 bytes}
+// (version 1 padded the row to 4 bytes only: odd entries of widths with width % 4 in {1, 2} were 4-byte aligned under 8-byte accesses)
 // Included by encode.cu (the builder reads the scratch of the last encode) and by decode.cu (constants only).
 #pragma once
 #include <stdint.h>
@@ -14,8 +15,9 @@ namespace felics {
 
 constexpr uint32_t SIDECAR_MAGIC = 0x43534C46u;   // "FLSC"
 constexpr uint32_t SIDECAR_HEADER_BYTES = 32;
+constexpr uint32_t SIDECAR_VERSION = 2;
 constexpr uint32_t SIDECAR_TABLE_WORDS = (NBIN - 1) * NK;
-inline size_t sidecar_entry_bytes(uint32_t w) { return 16 + (size_t)SIDECAR_TABLE_WORDS * 4 + (((size_t)w * 2 + 3) & ~(size_t)3); }
+inline size_t sidecar_entry_bytes(uint32_t w) { return 16 + (size_t)SIDECAR_TABLE_WORDS * 4 + (((size_t)w * 2 + 7) & ~(size_t)7); }   // a multiple of 8: every entry starts 8-byte aligned
 // rows per band must put every band start on a tile boundary (the encoder knows bit offsets and chain positions per tile)
 inline uint32_t sidecar_row_unit(uint32_t w) {
     uint32_t a = w, b = TILE;
@@ -131,7 +133,7 @@ int sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *h_out, size_t ca
     a.out = (uint8_t *)ctx->staging_out;
     k_sidecar<<<le.nch * nbands, NBIN, 0, ctx->stream>>>(a);
     uint32_t *hh = reinterpret_cast<uint32_t *>(h_out);
-    const uint32_t hdr[8] = {SIDECAR_MAGIC, 1u, le.w, le.h, le.nch, band_rows, nbands, (uint32_t)entry};
+    const uint32_t hdr[8] = {SIDECAR_MAGIC, SIDECAR_VERSION, le.w, le.h, le.nch, band_rows, nbands, (uint32_t)entry};
     memcpy(hh, hdr, sizeof(hdr));
     FELICS_CUDA_TRY(cudaMemcpyAsync(h_out + SIDECAR_HEADER_BYTES, a.out, total - SIDECAR_HEADER_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     FELICS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

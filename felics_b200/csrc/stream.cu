@@ -2,17 +2,23 @@
 //
 // The multi-kernel pipeline of encode.cu is built for a single big image: every stage is a kernel over the whole
 // plane and every intermediate (grouped residuals, grouped indices, code records ...) travels through HBM.  A batch
-// of small images does not need that: the estimator rows of an image (parameter_selection.rs:24-85) are 511 x 6
+// of small images does not need that: the estimator rows of an image (parameter_selection.rs:24-85) are 256 x 6
 // small counters, so a block can walk the image in raster order, band by band (4096 pixels), and keep everything it
 // needs between the pixels and the bit stream in shared memory:
 //
 //   load      band + the row above it, cp.async into shared memory (double buffered)
-//   classify  neighbours, context, class, residual of every pixel (misc.rs:6-24, compression.rs:118-145)
-//   rank      stable grouping of the band's out-of-range pixels by context: match_any ranks inside 32 consecutive
-//             pixels, per-warp counters, one prefix over the warps -> the band's "chains" (one per context)
-//   walk      KEstimator for every chain of the band, starting from the counters the previous band left: a warp
-//             walks a long chain 128 elements at a time (prefix sums of the six code costs, halvings found by ballot,
-//             exact for any data), short chains are walked one per lane
+//   group     every warp takes 512 consecutive pixels, 32 at a time with lane = pixel: neighbours, context, class and
+//             residual (misc.rs:6-24, compression.rs:118-145), then the stable rank of every out-of-range pixel among
+//             the warp's pixels of its context (match_any + one counter per context), one scan over the warp's
+//             counters, and the residuals land in the warp's region of the chain array, grouped by context, raster
+//             order kept.  A context's chain in this band = its segments in the eight regions, in warp order
+//   walk      KEstimator for every chain, starting from the counters the previous band left.  A long chain is cut
+//             into steps of 128 elements; a step is one task: any warp loads its elements, looks up their six code
+//             costs and prefix-sums them (all of that is independent of the counters), then waits until the step
+//             before it has published the counters, finds the halvings by ballot (counters only grow inside an epoch)
+//             and the k of every element, and publishes the counters for the next step -- so the steps of one chain
+//             are prepared side by side and only their short second halves run one after the other.  Short chains
+//             are walked one per lane, the reference's loop as written.  Exact for any data
 //   code      marker + phased-in / Rice code of every pixel (compression.rs:130-145) in registers, lengths scanned
 //   pack      MSB-first packing into a shared-memory window, whole words leave for the image's slot in HBM
 //
@@ -25,6 +31,7 @@
 #include "device_common.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -33,34 +40,42 @@ namespace felics {
 namespace {
 
 constexpr int SE_THREADS = 256;
+#ifndef SE_CTAS_PER_SM
+#define SE_CTAS_PER_SM 3
+#endif
 constexpr int SE_WARPS = SE_THREADS / 32;
 constexpr int SE_PPT = 16;                                  // pixels per thread in the code / pack phase
 constexpr int SE_BAND = SE_THREADS * SE_PPT;                // 4096 pixels per band
-constexpr int SE_WPIX = SE_BAND / SE_WARPS;                 // 512 consecutive pixels per warp in the rank phase
+constexpr int SE_WPIX = SE_BAND / SE_WARPS;                 // 512 consecutive pixels per warp in the group phase
 constexpr int SE_WSTEPS = SE_WPIX / 32;
 constexpr int SE_INFO_WORDS = SE_BAND + SE_BAND / 16 * 4;   // one word per pixel, 4 words of padding per 16 (bank spread)
-constexpr int SE_EC_BYTES = SE_BAND + NBIN * 4 + 256;       // chain starts are 4-aligned; slack for the walker's last load
+constexpr int SE_NCTX = 256;                                // contexts of 8-bit gray samples: H - L <= 255
+constexpr int SE_WREG = SE_WPIX + 3 * SE_NCTX;              // bytes of a warp's region of the chain array (segments are padded to 4)
 constexpr int SE_OUT_WORDS = 2048;                          // bit window: 65536 bits = 16 bits per pixel of a band
-constexpr uint32_t SE_LONG = 48;                            // chains this long (per band) are walked by a whole warp
+constexpr uint32_t SE_LONG = 32;                            // chains this long (padded, per band) are walked in 128-element steps
 constexpr uint32_t SE_HALVE_KEY = (HALVE_AT + 1u) << 3;     // key of a count that has passed 1024
 constexpr uint32_t SE_NONE = 0xFFFFFFFFu;
 constexpr uint32_t SE_MAX_W = 8192;                         // widest row whose predecessor fits in front of a band
+constexpr uint32_t SE_NULL_E = 255;                         // padding element of a chain segment (a gray residual is at most 254)
 
-// info word of a pixel:  [31:30] class (0 in range, 1 above, 2 below, 3 not coded)  [29:21] P-L | P-H-1 | L-P-1
-//                        [20:12] context  [11:0] rank inside the warp's pixels of that context (rank phase)
-// after the scatter an out-of-range pixel keeps [31:21] and carries its chain position in [12:0]
+// info word of a pixel:  [31] out of range  [30] above (with [31]); 01 = not coded  [29:21] P-L | P-H-1 | L-P-1
+//                        [20:12] context  [11:0] rank among the warp's pixels of that context, then position in the warp's region
+constexpr uint32_t SE_INFO_NONE = 0x40000000u;
 __device__ __forceinline__ uint32_t info_index(uint32_t p) { return p + ((p >> 4) << 2); }
 
 struct SeSmem {
     uint32_t info[SE_INFO_WORDS];
-    uint32_t state[NBIN][4];            // estimator row of a context: counts as u16 pairs (k0 | k1 << 16, k2 | k3 << 16, k4 | k5 << 16)
-    uint16_t wcnt[SE_WARPS][NBIN];      // per warp and context: count, then exclusive prefix over the warps
-    uint32_t cb[NBIN];                  // chain of a context in this band: base | count << 16
-    uint16_t longlist[NBIN], shortlist[NBIN];
-    uint32_t out[SE_OUT_WORDS + 4];
-    uint8_t ec[SE_EC_BYTES];            // residuals in chain order; the walk overwrites them with k
+    uint32_t wseg[SE_WARPS][SE_NCTX];   // per warp and context: count while ranking, then base << 16 | count inside the warp's region
+    uint32_t state[SE_NCTX][3];         // estimator row of a context: counts as u16 pairs (k0 | k1 << 16, k2 | k3 << 16, k4 | k5 << 16)
+    uint4 lut[SE_NCTX];                 // code costs of a residual under k = 0..5, times 8, as u16 pairs (nothing for SE_NULL_E)
+    uint32_t out[SE_OUT_WORDS + 4];     // the bit window
+    uint32_t stepdone[SE_NCTX];         // steps of a chain walked so far in this band
+    uint16_t longc[SE_NCTX];            // long chains of the band: context | steps << 8
+    uint16_t shortlist[SE_NCTX];
+    uint32_t roundcnt[40];              // chains that have a step s (a chain of a band has at most 34 steps)
+    uint8_t ec[SE_WARPS][SE_WREG];      // residuals grouped by context, one region per warp; the walk overwrites them with k
     uint32_t wsum[SE_WARPS];
-    uint32_t nlong, nshort, task, plane;
+    uint32_t ntask, nlong, nshort, task, plane;
 };
 
 struct StreamArgs {
@@ -73,6 +88,8 @@ struct StreamArgs {
     uint32_t w, h, npix, nplanes;
     uint32_t halo_cap;          // bytes in front of a band in the pixel buffer (>= w, multiple of 16)
     uint32_t vec16;             // pixels, w multiples of 16: 16-byte copies
+    uint32_t dbg;               // timing experiments only (FELICS_B200_STREAM_DBG): 1 no walk, 2 no code/pack, 4 no group/walk, 8 phase clocks
+    unsigned long long *clocks; // dbg & 8: cycles per phase, summed over the blocks (thread 0 of every block)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,17 +116,19 @@ __device__ __forceinline__ void load_band(uint8_t *buf, const StreamArgs &a, con
     cp_async_commit();
 }
 
-// compression.rs:118-145 for one pixel given its two neighbours
+// compression.rs:118-145 for one pixel given its two neighbours.  At most one of L-P-1 and P-H-1 is non-negative:
+// it is the residual of an out-of-range pixel; both negative = in range, the code is P-L.
 __device__ __forceinline__ uint32_t make_info(int p, int v1, int v2) {
     const int h = max(v1, v2), l = min(v1, v2);
-    const bool below = p < l, above = p > h;
-    const uint32_t cls = below ? 2u : (above ? 1u : 0u);
-    const int val = below ? l - p - 1 : (above ? p - h - 1 : p - l);
-    return (cls << 30) | ((uint32_t)val << 21) | ((uint32_t)(h - l) << 12);
+    const int below = l - p - 1, above = p - h - 1;
+    const int m = max(below, above);
+    const uint32_t val = (uint32_t)(m >= 0 ? m : p - l);
+    const uint32_t top = (~(uint32_t)(below & above) & 0x80000000u) | ((~(uint32_t)above >> 1) & 0x40000000u);   // [31] out of range, [30] above
+    return top | (val << 21) | ((uint32_t)(h - l) << 12);
 }
-// any pixel (misc.rs:6-24); pb = first pixel of the band, j = offset in the band, i = index in the plane
-__device__ __forceinline__ uint32_t classify_slow(const uint8_t *pb, int j, uint32_t i, uint32_t x, uint32_t y, int w, const uint8_t *plane) {
-    if (i < 2) return 3u << 30;
+// pixels of the first row and the first column (misc.rs:6-24); pb = first pixel of the band, j = offset in the band, i = index in the plane
+__device__ __noinline__ uint32_t classify_edge(const uint8_t *pb, int j, uint32_t i, uint32_t x, uint32_t y, int w, const uint8_t *plane) {
+    if (i < 2) return SE_INFO_NONE;
     const int p = pb[j];
     int v1, v2;
     if (x > 0 && y > 0) { v1 = pb[j - 1]; v2 = pb[j - w]; }
@@ -122,18 +141,19 @@ __device__ __forceinline__ uint32_t classify_slow(const uint8_t *pb, int j, uint
 // ---- estimator rows as keys: count * 8 + (5 - k).  The smallest key is the smallest count with ties going to the
 // largest k (get_k's `<=` scan, parameter_selection.rs:78-83); costs are added as cost * 8.
 __device__ __forceinline__ void load_state(const uint32_t *row, uint32_t (&v)[NK]) {
-    const uint4 s = *reinterpret_cast<const uint4 *>(row);
-    v[0] = ((s.x & 0xffffu) << 3) | 5u; v[1] = ((s.x >> 16) << 3) | 4u;
-    v[2] = ((s.y & 0xffffu) << 3) | 3u; v[3] = ((s.y >> 16) << 3) | 2u;
-    v[4] = ((s.z & 0xffffu) << 3) | 1u; v[5] = ((s.z >> 16) << 3);
+    const uint32_t s0 = row[0], s1 = row[1], s2 = row[2];
+    v[0] = ((s0 & 0xffffu) << 3) | 5u; v[1] = ((s0 >> 16) << 3) | 4u;
+    v[2] = ((s1 & 0xffffu) << 3) | 3u; v[3] = ((s1 >> 16) << 3) | 2u;
+    v[4] = ((s2 & 0xffffu) << 3) | 1u; v[5] = ((s2 >> 16) << 3);
 }
 __device__ __forceinline__ void store_state(uint32_t *row, const uint32_t (&v)[NK]) {
     // counts stay below 2^16 for 8-bit data: c0 <= 25 * (1024 + 510)
-    *reinterpret_cast<uint4 *>(row) = make_uint4((v[0] >> 3) | ((v[1] >> 3) << 16), (v[2] >> 3) | ((v[3] >> 3) << 16), (v[4] >> 3) | ((v[5] >> 3) << 16), 0u);
+    row[0] = (v[0] >> 3) | ((v[1] >> 3) << 16); row[1] = (v[2] >> 3) | ((v[3] >> 3) << 16); row[2] = (v[4] >> 3) | ((v[5] >> 3) << 16);
 }
-__device__ __forceinline__ void cost_keys(uint32_t e, uint32_t (&c)[NK]) {   // rice_coding.rs:56-58 times 8
-#pragma unroll
-    for (int k = 0; k < NK; k++) c[k] = ((e >> k) + 1u + (uint32_t)k) << 3;
+// the six code costs (e >> k) + 1 + k of a residual (rice_coding.rs:56-58), times 8, from the table
+__device__ __forceinline__ void cost_keys(const uint4 *lut, uint32_t e, uint32_t (&c)[NK]) {
+    const uint4 t = lut[e];
+    c[0] = t.x & 0xffffu; c[1] = t.x >> 16; c[2] = t.y & 0xffffu; c[3] = t.y >> 16; c[4] = t.z & 0xffffu; c[5] = t.z >> 16;
 }
 __device__ __forceinline__ uint32_t min6(const uint32_t (&v)[NK]) { return min(min(min(v[0], v[1]), min(v[2], v[3])), min(v[4], v[5])); }
 __device__ __forceinline__ void halve_keys(uint32_t (&v)[NK]) {              // parameter_selection.rs:58-63
@@ -141,126 +161,161 @@ __device__ __forceinline__ void halve_keys(uint32_t (&v)[NK]) {              // 
     for (int k = 0; k < NK; k++) v[k] = ((v[k] >> 4) << 3) | (uint32_t)(5 - k);
 }
 
-// one chain per lane (short chains): the reference's loop as written
+// one chain per lane (short chains): the reference's loop as written, segment after segment
 __device__ __forceinline__ void serial_walk(SeSmem &S, uint32_t c) {
     if (c == SE_NONE) return;
-    const uint32_t cbv = S.cb[c];
-    const uint32_t base = cbv & 0xffffu, n = cbv >> 16;
     uint32_t st[NK];
     load_state(S.state[c], st);
     uint32_t m = min6(st);
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t e = S.ec[base + i];
-        S.ec[base + i] = (uint8_t)(5u - (m & 7u));
-        uint32_t c6[NK];
-        cost_keys(e, c6);
+    for (int q = 0; q < SE_WARPS; q++) {
+        const uint32_t sw = S.wseg[q][c];
+        uint8_t *seg = S.ec[q] + (sw >> 16);
+        const uint32_t n = sw & 0xffffu;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t e = seg[i];
+            seg[i] = (uint8_t)(5u - (m & 7u));
+            uint32_t c6[NK];
+            cost_keys(S.lut, e, c6);
 #pragma unroll
-        for (int k = 0; k < NK; k++) st[k] += c6[k];
-        m = min6(st);
-        if (m >= SE_HALVE_KEY) { halve_keys(st); m = min6(st); }
+            for (int k = 0; k < NK; k++) st[k] += c6[k];
+            m = min6(st);
+            if (m >= SE_HALVE_KEY) { halve_keys(st); m = min6(st); }
+        }
     }
     store_state(S.state[c], st);
 }
 
-// one chain per warp, 128 elements per step (four consecutive elements per lane).  With T the prefix sum of the costs
-// inside the step, the counters before element g are B + T(g) as long as no halving lies between; the first element
-// after which all six counters have passed 1024 is found by one ballot (counters only grow inside an epoch), the
-// halved counters become the new base for the elements behind it, and the search repeats.
-__device__ __forceinline__ void coop_walk(SeSmem &S, uint32_t c, uint32_t lane) {
-    const uint32_t cbv = S.cb[c];
-    const uint32_t base = cbv & 0xffffu, n = cbv >> 16;
-    uint32_t st[NK];
-    load_state(S.state[c], st);
-    uint32_t *ec4 = reinterpret_cast<uint32_t *>(S.ec + base);
-    for (uint32_t s0 = 0; s0 < n; s0 += 128) {
-        const uint32_t word = ec4[(s0 >> 2) + lane];
-        const int nvalid = min(4, max(0, (int)n - (int)s0 - 4 * (int)lane));
-        uint32_t P[4][NK];   // inclusive cost prefix inside my four elements
+// One step of a long chain: 128 consecutive elements of the chain (four per lane; the chain is the concatenation of its
+// segments in the eight warp regions, every segment padded to a multiple of four with null elements that cost nothing).
+// With T the prefix sum of the costs inside the step, the counters before element g are B + T(g) as long as no halving
+// lies between; the first element after which all six counters have passed 1024 is found by one ballot (counters only
+// grow inside an epoch), the halved counters become the new base for the elements behind it, and the search repeats.
+__device__ __forceinline__ void coop_step(SeSmem &S, uint32_t c, uint32_t step, uint32_t lane) {
+    // where my four elements live
+    const uint32_t sw = lane < SE_WARPS ? S.wseg[lane][c] : 0u;
+    const uint32_t pc = ((sw & 0xffffu) + 3u) & ~3u;          // padded length of segment `lane`
+    uint32_t incl = pc;
+#pragma unroll
+    for (int o = 1; o < SE_WARPS; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t v = step * 128u + 4u * lane;               // my first element's index in the chain
+    uint32_t seg = 0;
+#pragma unroll
+    for (int q = 0; q < SE_WARPS - 1; q++) seg += __shfl_sync(0xffffffffu, incl, q) <= v ? 1u : 0u;
+    const uint32_t vtot = __shfl_sync(0xffffffffu, incl, SE_WARPS - 1);
+    const uint32_t seg_first = __shfl_sync(0xffffffffu, incl - pc, seg), seg_base = __shfl_sync(0xffffffffu, sw >> 16, seg);
+    const bool valid = v < vtot;
+    uint32_t *slot = reinterpret_cast<uint32_t *>(S.ec[seg] + seg_base + (v - seg_first));
+    const uint32_t word = valid ? *slot : 0xffffffffu;
+
+    uint32_t P[4][NK];   // inclusive cost prefix inside my four elements
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t c6[NK];
+        cost_keys(S.lut, (word >> (8 * j)) & 255u, c6);
+#pragma unroll
+        for (int k = 0; k < NK; k++) P[j][k] = j ? P[j - 1][k] + c6[k] : c6[k];
+    }
+    // exclusive prefix of the lane totals over the warp, two 16-bit sums per register (128 * 255 < 65536)
+    const uint32_t t01 = (P[3][0] >> 3) | ((P[3][1] >> 3) << 16), t23 = (P[3][2] >> 3) | ((P[3][3] >> 3) << 16), t45 = (P[3][4] >> 3) | ((P[3][5] >> 3) << 16);
+    uint32_t x01 = t01, x23 = t23, x45 = t45;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, x01, o), b = __shfl_up_sync(0xffffffffu, x23, o), d = __shfl_up_sync(0xffffffffu, x45, o);
+        if (lane >= (uint32_t)o) { x01 += a; x23 += b; x45 += d; }
+    }
+    x01 -= t01; x23 -= t23; x45 -= t45;
+    const uint32_t X[NK] = {(x01 & 0xffffu) << 3, (x01 >> 16) << 3, (x23 & 0xffffu) << 3, (x23 >> 16) << 3, (x45 & 0xffffu) << 3, (x45 >> 16) << 3};
+
+    // everything above is independent of the counters: now wait for the step before this one
+    if (step) {
+        while (*reinterpret_cast<volatile uint32_t *>(&S.stepdone[c]) < step) __nanosleep(100);
+        __threadfence_block();
+    }
+    uint32_t B[NK];
+    load_state(S.state[c], B);
+#pragma unroll
+    for (int k = 0; k < NK; k++) B[k] += X[k];
+    uint32_t kw = 0;
+    int done = 0;   // elements of the step already behind a halving: their k is final
+    for (;;) {
+        uint32_t m[5];
+        m[0] = min6(B);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            uint32_t c6[NK];
-            cost_keys((word >> (8 * j)) & 255u, c6);
+            uint32_t t[NK];
 #pragma unroll
-            for (int k = 0; k < NK; k++) {
-                const uint32_t v = j < nvalid ? c6[k] : 0u;
-                P[j][k] = j ? P[j - 1][k] + v : v;
-            }
+            for (int k = 0; k < NK; k++) t[k] = B[k] + P[j][k];
+            m[j + 1] = min6(t);
         }
-        // exclusive prefix of the lane totals over the warp, two 16-bit sums per register (128 * 510 < 65536)
-        uint32_t t01 = (P[3][0] >> 3) | ((P[3][1] >> 3) << 16), t23 = (P[3][2] >> 3) | ((P[3][3] >> 3) << 16), t45 = (P[3][4] >> 3) | ((P[3][5] >> 3) << 16);
-        uint32_t x01 = t01, x23 = t23, x45 = t45;
+        const uint32_t knew = (5u - (m[0] & 7u)) | ((5u - (m[1] & 7u)) << 8) | ((5u - (m[2] & 7u)) << 16) | ((5u - (m[3] & 7u)) << 24);
+        const int sh = done - 4 * (int)lane;   // how many of my elements are final
+        const uint32_t mask = sh <= 0 ? 0xffffffffu : (sh >= 4 ? 0u : 0xffffffffu << (8 * sh));
+        kw = (kw & ~mask) | (knew & mask);
+        int first = 4;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, x01, o), b = __shfl_up_sync(0xffffffffu, x23, o), d = __shfl_up_sync(0xffffffffu, x45, o);
-            if (lane >= (uint32_t)o) { x01 += a; x23 += b; x45 += d; }
+        for (int j = 3; j >= 0; j--)
+            if (m[j + 1] >= SE_HALVE_KEY && j >= sh) first = j;
+        const uint32_t bal = __ballot_sync(0xffffffffu, first < 4);
+        if (!bal) break;
+        const int L = __ffs(bal) - 1;
+        const int jh = __shfl_sync(0xffffffffu, first, L);
+        uint32_t after[NK], tin[NK];
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            const uint32_t pj = jh == 0 ? P[0][k] : (jh == 1 ? P[1][k] : (jh == 2 ? P[2][k] : P[3][k]));
+            after[k] = B[k] + pj;
+            tin[k] = X[k] + pj;
         }
-        x01 -= t01; x23 -= t23; x45 -= t45;
-        const uint32_t X[NK] = {(x01 & 0xffffu) << 3, (x01 >> 16) << 3, (x23 & 0xffffu) << 3, (x23 >> 16) << 3, (x45 & 0xffffu) << 3, (x45 >> 16) << 3};
-        uint32_t B[NK];
+        halve_keys(after);
 #pragma unroll
-        for (int k = 0; k < NK; k++) B[k] = st[k] + X[k];
-        uint32_t kw = 0;
-        int done = 0;   // elements of the step already behind a halving: their k is final
-        for (;;) {
-            uint32_t m[5];
-            m[0] = min6(B);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t t[NK];
-#pragma unroll
-                for (int k = 0; k < NK; k++) t[k] = B[k] + P[j][k];
-                m[j + 1] = min6(t);
-            }
-            const uint32_t knew = (5u - (m[0] & 7u)) | ((5u - (m[1] & 7u)) << 8) | ((5u - (m[2] & 7u)) << 16) | ((5u - (m[3] & 7u)) << 24);
-            const int sh = done - 4 * (int)lane;   // how many of my elements are final
-            const uint32_t mask = sh <= 0 ? 0xffffffffu : (sh >= 4 ? 0u : 0xffffffffu << (8 * sh));
-            kw = (kw & ~mask) | (knew & mask);
-            int first = 4;
-#pragma unroll
-            for (int j = 3; j >= 0; j--)
-                if (m[j + 1] >= SE_HALVE_KEY && j < nvalid && j >= sh) first = j;
-            const uint32_t bal = __ballot_sync(0xffffffffu, first < 4);
-            if (!bal) break;
-            const int L = __ffs(bal) - 1;
-            const int jh = __shfl_sync(0xffffffffu, first, L);
-            uint32_t after[NK], tin[NK];
-#pragma unroll
-            for (int k = 0; k < NK; k++) {
-                const uint32_t pj = jh == 0 ? P[0][k] : (jh == 1 ? P[1][k] : (jh == 2 ? P[2][k] : P[3][k]));
-                after[k] = B[k] + pj;
-                tin[k] = X[k] + pj;
-            }
-            halve_keys(after);
-#pragma unroll
-            for (int k = 0; k < NK; k++) {
-                const uint32_t av = __shfl_sync(0xffffffffu, after[k], L), tv = __shfl_sync(0xffffffffu, tin[k], L);
-                B[k] = av + X[k] - tv;   // counters before my first element, for lanes behind the halving
-            }
-            done = 4 * L + jh + 1;
+        for (int k = 0; k < NK; k++) {
+            const uint32_t av = __shfl_sync(0xffffffffu, after[k], L), tv = __shfl_sync(0xffffffffu, tin[k], L);
+            B[k] = av + X[k] - tv;   // counters before my first element, for lanes behind the halving
         }
-        if (nvalid > 0) ec4[(s0 >> 2) + lane] = kw;
-#pragma unroll
-        for (int k = 0; k < NK; k++) st[k] = __shfl_sync(0xffffffffu, B[k] + P[3][k], 31);
+        done = 4 * L + jh + 1;
     }
-    if (lane == 0) store_state(S.state[c], st);
+    if (valid) *slot = kw;
+    uint32_t st[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) st[k] = __shfl_sync(0xffffffffu, B[k] + P[3][k], 31);
+    if (lane == 0) {
+        store_state(S.state[c], st);
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(&S.stepdone[c]) = step + 1u;
+    }
 }
 
-// code record of a pixel (device_common.cuh: length << 22 | payload)
-__device__ __forceinline__ uint32_t make_record(uint32_t wd, const uint8_t *ec) {
-    const uint32_t cls = wd >> 30;
-    if (cls == 3u) return 0u;
+// code record of a pixel: length << 22 | payload.  length <= 22: the payload is the whole code word, right aligned
+// (in range: '1' marker + phased-in code, phase_in_coding.rs:64-84; out of range: '0', above, q ones, '0', k remainder bits,
+// rice_coding.rs:26-39).  Longer codes (long unary runs) carry above << 12 | k << 9 | e and are expanded by the packer.
+// Straight-line code: both classes are evaluated for every pixel and selected, a divergent branch costs more.
+__device__ __forceinline__ uint32_t make_record(uint32_t wd, const uint8_t *ecw) {
+    const uint32_t top = wd >> 30;                       // 0 in range, 1 not coded, 2 below, 3 above
     const uint32_t val = (wd >> 21) & 511u;
-    if (cls == 0u) {
-        int len;
-        const uint32_t code = phase_in_code(((wd >> 12) & 511u) + 1u, val, len);
-        return ((uint32_t)(len + 1) << 22) | (1u << len) | code;            // '1' marker then the phased-in code
-    }
-    const uint32_t k = ec[wd & 8191u];
-    const uint32_t q = val >> k, rem = val & ((1u << k) - 1u);
-    const uint32_t above = cls == 1u ? 1u : 0u;
-    const uint32_t len = 2u + q + 1u + k;
-    if (len <= (uint32_t)REC_SHORT_MAX) return (len << 22) | (above << (q + 1u + k)) | (((1u << q) - 1u) << (k + 1u)) | rem;
-    return (len << 22) | (above << 17) | (k << 14) | (rem << 9) | q;
+    const bool oor = top >= 2u;
+    // in range: x = (v + n - left_p) mod n = (v + 2^m) mod n; short codes (x < right_p) have m bits, the others m + 1 bits holding x + right_p
+    const uint32_t n = ((wd >> 12) & 511u) + 1u;
+    const uint32_t m = 31u - (uint32_t)__clz(n);
+    const uint32_t p2 = 1u << m;
+    uint32_t x = val + p2;
+    x = min(x, x - n);
+    const uint32_t rp = 2u * p2 - n;
+    const bool lng = x >= rp;
+    const uint32_t rin = ((m + 1u + (lng ? 1u : 0u)) << 22) + x + (lng ? rp + 2u * p2 : p2);
+    // out of range
+    const uint32_t k = ecw[oor ? (wd & 0xfffu) : 0u] & 7u;
+    const uint32_t q = val >> k;
+    const uint32_t rem = val - (q << k);
+    const uint32_t len = q + k + 3u;
+    const uint32_t ones = ((top - 1u) << min(q, 24u)) - 1u;   // above: q + 1 ones, the top one is the `above` bit; below: q ones
+    const uint32_t rshort = (len << 22) | (ones << (k + 1u)) | rem;
+    const uint32_t rlong = (len << 22) | ((top & 1u) << 12) | (k << 9) | val;
+    const uint32_t roor = len <= (uint32_t)REC_SHORT_MAX ? rshort : rlong;
+    const uint32_t r = oor ? roor : rin;
+    return top == 1u ? 0u : r;
 }
 
 // bits [off, off + n) of the band's stream, clipped to the window [w0, w1)
@@ -273,29 +328,44 @@ __device__ __forceinline__ void put_clipped(uint32_t *out, uint32_t off, uint32_
     put_bits_smem(out, lo - w0, v, (int)nb);
 }
 template <typename PUT>
-__device__ __forceinline__ void emit_fields(uint32_t r, uint32_t off, PUT put) {
+__device__ __forceinline__ void emit_fields(uint32_t r, uint32_t off, PUT put) {   // any record, field by field
     const uint32_t len = rec_len(r);
     if (len == 0) return;
     if (len <= (uint32_t)REC_SHORT_MAX) { put(off, r & 0x3fffffu, len); return; }
-    uint32_t q = r & 511u;
-    const uint32_t rem = (r >> 9) & 31u, k = (r >> 14) & 7u, above = (r >> 17) & 1u;
+    const uint32_t e = r & 511u, k = (r >> 9) & 7u, above = (r >> 12) & 1u;
+    uint32_t q = e >> k;
     put(off, above, 2u);   // '0', above
     off += 2;
     while (q >= 32) { put(off, 0xffffffffu, 32u); off += 32; q -= 32; }
     if (q) { put(off, (1u << q) - 1u, q); off += q; }
-    put(off, rem, k + 1u);   // '0' then k remainder bits
+    put(off, e & ((1u << k) - 1u), k + 1u);   // '0' then k remainder bits
 }
 
-__global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
+// a long unary run (more than 22 bits) straight into the window, field by field; rare, kept out of the packer's loop
+__device__ __noinline__ void pack_long(uint32_t *out, uint32_t r, uint32_t at) {
+    emit_fields(r, at, [&](uint32_t off, uint32_t val, uint32_t nb) { put_bits_smem(out, off, val, (int)nb); });
+}
+
+__global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(StreamArgs a) {
     extern __shared__ __align__(16) unsigned char se_smem[];
     SeSmem &S = *reinterpret_cast<SeSmem *>(se_smem);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     const uint32_t buf_bytes = a.halo_cap + SE_BAND + 16u;
     uint8_t *const pixbuf0 = se_smem + ((sizeof(SeSmem) + 15) & ~(size_t)15);   // two buffers of buf_bytes
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t step_q = (4u * SE_THREADS) / a.w, step_r = (4u * SE_THREADS) - step_q * a.w;
     const uint32_t slot_words = (uint32_t)(a.slot_bytes >> 2);
     const int w = (int)a.w;
+    long long tclk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+    const bool clk = (a.dbg & 8u) && tid == 0;
+#define SE_CLK(i) do { if (clk) { const long long t_ = clock64(); tclk[i] += t_ - tlast; tlast = t_; } } while (0)
+
+    // code costs of every residual (rice_coding.rs:56-58) under k = 0..5, times 8 (the estimator keys of coop_step)
+    for (uint32_t e = tid; e < SE_NCTX; e += SE_THREADS) {
+        uint32_t c[NK];
+#pragma unroll
+        for (int k = 0; k < NK; k++) c[k] = e == SE_NULL_E ? 0u : ((e >> k) + 1u + (uint32_t)k) << 3;
+        S.lut[e] = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), 0u);
+    }
 
     for (;;) {
         __syncthreads();
@@ -306,7 +376,7 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
         const uint8_t *plane = a.pixels + (size_t)p * a.npix;
         uint32_t *slot = reinterpret_cast<uint32_t *>(a.temp + (size_t)p * a.slot_bytes);
 
-        for (uint32_t i = tid; i < NBIN * 4; i += SE_THREADS) (&S.state[0][0])[i] = 0u;
+        for (uint32_t i = tid; i < SE_NCTX * 3; i += SE_THREADS) (&S.state[0][0])[i] = 0u;
         // header (format.rs:51-61) and the two raw samples (compression.rs:93-108): 22 bytes = five words and a half
         const uint32_t v0 = a.npix >= 1 ? plane[0] : 0u, v1 = a.npix >= 2 ? plane[1] : 0u;
         if (tid == 0) {
@@ -324,119 +394,130 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
         for (uint32_t b = 0; b < nbands; b++) {
             const uint32_t start = b * SE_BAND, cnt = min((uint32_t)SE_BAND, a.npix - start);
             const uint8_t *pb = pixbuf0 + (b & 1u) * buf_bytes + a.halo_cap;
+            if (clk) tlast = clock64();
             cp_async_wait_all();
             __syncthreads();
+            SE_CLK(0);
             if (b + 1 < nbands) load_band(pixbuf0 + ((b + 1) & 1u) * buf_bytes, a, plane, start + SE_BAND, min((uint32_t)SE_BAND, a.npix - start - SE_BAND));
+            if (tid == 0) { S.ntask = 0; S.nlong = 0; S.nshort = 0; S.task = 0; }
+            if (tid < 40) S.roundcnt[tid] = 0u;
 
-            // ---- classify: four consecutive pixels per thread ------------------------------------------------
-            for (uint32_t i = tid; i < SE_WARPS * NBIN / 2; i += SE_THREADS) reinterpret_cast<uint32_t *>(&S.wcnt[0][0])[i] = 0u;
-            if (tid == 0) { S.nlong = 0; S.nshort = 0; S.task = 0; }
-            {
-                const uint32_t i0 = start + 4u * tid;
-                uint32_t y = i0 / a.w, x = i0 - y * a.w;
+            // ---- group: classify, rank and scatter, every warp on its own 512 pixels --------------------------------
+            if (!(a.dbg & 4u)) {
+                uint32_t *cntw = S.wseg[wid];
+                uint8_t *ecw = S.ec[wid];
 #pragma unroll
-                for (int it = 0; it < SE_PPT / 4; it++) {
-                    const uint32_t j = (uint32_t)it * 4u * SE_THREADS + 4u * tid;
-                    uint4 o = make_uint4(3u << 30, 3u << 30, 3u << 30, 3u << 30);
-                    if (j < cnt) {
-                        if (x >= 4 && y >= 1) {
-                            const uint32_t cur = *reinterpret_cast<const uint32_t *>(pb + j), up = *reinterpret_cast<const uint32_t *>(pb + (int)j - w);
-                            const int left = pb[(int)j - 1];
-                            const int c0 = cur & 255u, c1 = (cur >> 8) & 255u, c2 = (cur >> 16) & 255u, c3 = cur >> 24;
-                            o.x = make_info(c0, left, up & 255u);
-                            o.y = make_info(c1, c0, (up >> 8) & 255u);
-                            o.z = make_info(c2, c1, (up >> 16) & 255u);
-                            o.w = make_info(c3, c2, up >> 24);
-                        } else {
-                            o.x = classify_slow(pb, (int)j, start + j, x, y, w, plane);
-                            o.y = classify_slow(pb, (int)j + 1, start + j + 1, x + 1, y, w, plane);
-                            o.z = classify_slow(pb, (int)j + 2, start + j + 2, x + 2, y, w, plane);
-                            o.w = classify_slow(pb, (int)j + 3, start + j + 3, x + 3, y, w, plane);
+                for (int q = 0; q < SE_NCTX / 32; q++) cntw[q * 32 + lane] = 0u;
+#pragma unroll
+                for (int q = 0; q < SE_WREG / 128; q++) reinterpret_cast<uint32_t *>(ecw)[q * 32 + lane] = 0xffffffffu;   // null elements
+                __syncwarp();
+                const uint32_t wp0 = wid * SE_WPIX;
+                {
+                    const uint32_t i0 = start + wp0 + lane;
+                    uint32_t y = i0 / a.w, x = i0 - y * a.w;
+#pragma unroll 2
+                    for (int s = 0; s < SE_WSTEPS; s++) {
+                        const uint32_t j = wp0 + 32u * s + lane;
+                        uint32_t wd = SE_INFO_NONE;
+                        if (j < cnt) {
+                            if (x > 0 && y > 0) wd = make_info(pb[j], pb[(int)j - 1], pb[(int)j - w]);
+                            else wd = classify_edge(pb, (int)j, start + j, x, y, w, plane);
                         }
+                        const bool oor = wd >> 31;
+                        const uint32_t act = __ballot_sync(0xffffffffu, oor);
+                        if (act) {
+                            if (oor) {
+                                const uint32_t delta = (wd >> 12) & 255u;
+                                const uint32_t grp = __match_any_sync(act, delta);
+                                const int leader = __ffs(grp) - 1;
+                                uint32_t prev = 0;
+                                if ((int)lane == leader) { prev = cntw[delta]; cntw[delta] = prev + __popc(grp); }
+                                prev = __shfl_sync(act, prev, leader);
+                                wd |= prev + __popc(grp & lt);
+                            }
+                            __syncwarp();
+                        }
+                        S.info[info_index(j)] = wd;
+                        x += 32;
+                        while (x >= a.w) { x -= a.w; y++; }
                     }
-                    *reinterpret_cast<uint4 *>(&S.info[info_index(j)]) = o;
-                    x += step_r; y += step_q;
-                    if (x >= a.w) { x -= a.w; y++; }
                 }
-            }
-            __syncthreads();
-
-            // ---- rank: stable position of every out-of-range pixel among the warp's pixels of its context ------
-            for (int s = 0; s < SE_WSTEPS; s++) {
-                const uint32_t ix = info_index(wid * SE_WPIX + s * 32 + lane);
-                const uint32_t wd = S.info[ix];
-                const bool oor = ((wd >> 30) - 1u) < 2u;
-                const uint32_t act = __ballot_sync(0xffffffffu, oor);
-                if (act == 0) continue;
-                const uint32_t delta = (wd >> 12) & 511u;
-                uint32_t grp = 0, prev = 0;
-                if (oor) {
-                    grp = __match_any_sync(act, delta);
-                    prev = S.wcnt[wid][delta];
+                // bases of the warp's segments: exclusive prefix of the counts, every segment padded to a multiple of four
+                {
+                    uint4 *c4 = reinterpret_cast<uint4 *>(cntw + 8u * lane);
+                    const uint4 ca = c4[0], cb4 = c4[1];
+                    const uint32_t n[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
+                    uint32_t sum = 0, ex[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { ex[q] = sum; sum += (n[q] + 3u) & ~3u; }
+                    uint32_t inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (uint32_t)o) inc += t;
+                    }
+                    const uint32_t base = inc - sum;
+                    c4[0] = make_uint4(((base + ex[0]) << 16) | n[0], ((base + ex[1]) << 16) | n[1], ((base + ex[2]) << 16) | n[2], ((base + ex[3]) << 16) | n[3]);
+                    c4[1] = make_uint4(((base + ex[4]) << 16) | n[4], ((base + ex[5]) << 16) | n[5], ((base + ex[6]) << 16) | n[6], ((base + ex[7]) << 16) | n[7]);
                 }
                 __syncwarp();
-                if (oor) {
-                    if ((grp & lt) == 0) S.wcnt[wid][delta] = (uint16_t)(prev + __popc(grp));
-                    S.info[ix] = wd | (prev + __popc(grp & lt));
+#pragma unroll 4
+                for (int s = 0; s < SE_WSTEPS; s++) {
+                    uint32_t *iw = &S.info[info_index(wp0 + 32u * s + lane)];
+                    const uint32_t wd = *iw;
+                    if (wd >> 31) {
+                        const uint32_t pos = (cntw[(wd >> 12) & 255u] >> 16) + (wd & 0xfffu);
+                        ecw[pos] = (uint8_t)((wd >> 21) & 511u);
+                        *iw = (wd & 0xffe00000u) | pos;
+                    }
                 }
-                __syncwarp();
+            } else {
+                for (int s = 0; s < SE_WSTEPS; s++) S.info[info_index(wid * SE_WPIX + 32u * s + lane)] = SE_INFO_NONE;
             }
             __syncthreads();
+            SE_CLK(1);
 
-            // ---- chains: exclusive prefix over the warps, chain bases, work lists ------------------------------
-            {
-                uint32_t run0 = 0, run1 = 0;
+            // ---- chains: one thread per context: length of its chain in this band, work lists -------------------------
+            if (!(a.dbg & 4u)) {
+                uint32_t vlen = 0;
 #pragma unroll
-                for (int q = 0; q < SE_WARPS; q++) {
-                    uint32_t *pw = reinterpret_cast<uint32_t *>(&S.wcnt[q][2 * tid]);
-                    const uint32_t v = *pw;
-                    *pw = run0 | (run1 << 16);
-                    run0 += v & 0xffffu; run1 += v >> 16;
-                }
-                const uint32_t a0 = (run0 + 3u) & ~3u, a1 = (run1 + 3u) & ~3u;
-                uint32_t inc = a0 + a1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= (uint32_t)o) inc += t;
-                }
-                if (lane == 31) S.wsum[wid] = inc;
-                __syncthreads();
-                uint32_t excl = inc - (a0 + a1);
-                for (uint32_t q = 0; q < wid; q++) excl += S.wsum[q];
-                S.cb[2 * tid] = excl | (run0 << 16);
-                S.cb[2 * tid + 1] = (excl + a0) | (run1 << 16);
-                if (run0 >= SE_LONG) S.longlist[atomicAdd(&S.nlong, 1u)] = (uint16_t)(2 * tid);
-                else if (run0) S.shortlist[atomicAdd(&S.nshort, 1u)] = (uint16_t)(2 * tid);
-                if (run1 >= SE_LONG) S.longlist[atomicAdd(&S.nlong, 1u)] = (uint16_t)(2 * tid + 1);
-                else if (run1) S.shortlist[atomicAdd(&S.nshort, 1u)] = (uint16_t)(2 * tid + 1);
-            }
-            __syncthreads();
-
-            // ---- scatter: residuals into chain order, chain position into the pixel's word ---------------------
-            for (int s = 0; s < SE_WSTEPS; s++) {
-                const uint32_t ix = info_index(wid * SE_WPIX + s * 32 + lane);
-                const uint32_t wd = S.info[ix];
-                if (((wd >> 30) - 1u) < 2u) {
-                    const uint32_t delta = (wd >> 12) & 511u;
-                    const uint32_t pos = (S.cb[delta] & 0xffffu) + S.wcnt[wid][delta] + (wd & 0xfffu);
-                    S.ec[pos] = (uint8_t)((wd >> 21) & 511u);
-                    S.info[ix] = (wd & 0xffe00000u) | pos;
+                for (int q = 0; q < SE_WARPS; q++) vlen += ((S.wseg[q][tid] & 0xffffu) + 3u) & ~3u;
+                if (vlen >= SE_LONG) {
+                    const uint32_t nst = (vlen + 127u) >> 7;
+                    S.longc[atomicAdd(&S.nlong, 1u)] = (uint16_t)(tid | (nst << 8));
+                    atomicAdd(&S.ntask, nst);
+                    for (uint32_t s = 0; s < nst; s++) atomicAdd(&S.roundcnt[s], 1u);
+                    S.stepdone[tid] = 0u;
+                } else if (vlen) {
+                    S.shortlist[atomicAdd(&S.nshort, 1u)] = (uint16_t)tid;
                 }
             }
             __syncthreads();
+            SE_CLK(2);
 
-            // ---- walk: long chains one per warp, short chains one per lane ------------------------------------
-            {
-                const uint32_t nl = S.nlong, ns = S.nshort;
+            // ---- walk: steps of long chains as tasks, short chains one per lane -----------------------------------------
+            if (!(a.dbg & 1u)) {
+                const uint32_t nt = S.ntask, nl = S.nlong, ns = S.nshort;
                 for (;;) {
                     uint32_t t = 0;
                     if (lane == 0) t = atomicAdd(&S.task, 1u);
                     t = __shfl_sync(0xffffffffu, t, 0);
-                    if (t < nl) {
-                        coop_walk(S, S.longlist[t], lane);
+                    if (t < nt) {
+                        // tasks in step-major order (step 0 of every long chain, then step 1 of those that have one, ...): by the
+                        // time a warp has prepared step s of a chain, step s - 1 was claimed a round earlier and is done or nearly
+                        uint32_t s = 0, i = t;
+                        for (uint32_t n = S.roundcnt[0]; i >= n; n = S.roundcnt[++s]) i -= n;
+                        uint32_t c = 0;
+                        for (uint32_t base = 0;; base += 32) {   // the i-th long chain that has a step s
+                            const uint32_t e = base + lane < nl ? (uint32_t)S.longc[base + lane] : 0u;
+                            const uint32_t bal = __ballot_sync(0xffffffffu, (e >> 8) > s);
+                            const uint32_t nb = __popc(bal);
+                            if (i < nb) { c = __shfl_sync(0xffffffffu, e, __fns(bal, 0, i + 1)) & 255u; break; }
+                            i -= nb;
+                        }
+                        coop_step(S, c, s, lane);
                     } else {
-                        const uint32_t si = (t - nl) * 32u;
+                        const uint32_t si = (t - nt) * 32u;
                         if (si >= ns) break;
                         serial_walk(S, si + lane < ns ? (uint32_t)S.shortlist[si + lane] : SE_NONE);
                         __syncwarp();
@@ -445,18 +526,22 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
             }
             // zero the bit window while the walkers finish (its last reader was the previous band's flush)
             for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) S.out[i] = 0u;
+            SE_CLK(3);
             __syncthreads();
+            SE_CLK(4);
 
             // ---- code: 16 consecutive pixels per thread, records stay in registers -------------------------------
             uint32_t r[SE_PPT];
             uint32_t mylen = 0;
             {
                 const uint4 *iw = reinterpret_cast<const uint4 *>(&S.info[info_index(tid * SE_PPT)]);
+                const uint8_t *ecw = S.ec[tid >> 5];   // the warp region my 16 pixels were grouped into: (16 * tid) / 512
 #pragma unroll
                 for (int q = 0; q < SE_PPT / 4; q++) {
                     const uint4 v = iw[q];
-                    r[4 * q] = make_record(v.x, S.ec); r[4 * q + 1] = make_record(v.y, S.ec);
-                    r[4 * q + 2] = make_record(v.z, S.ec); r[4 * q + 3] = make_record(v.w, S.ec);
+                    if (a.dbg & 2u) { r[4 * q] = r[4 * q + 1] = r[4 * q + 2] = r[4 * q + 3] = (v.x & 1u) << 22; continue; }
+                    r[4 * q] = make_record(v.x, ecw); r[4 * q + 1] = make_record(v.y, ecw);
+                    r[4 * q + 2] = make_record(v.z, ecw); r[4 * q + 3] = make_record(v.w, ecw);
                 }
 #pragma unroll
                 for (int q = 0; q < SE_PPT; q++) mylen += rec_len(r[q]);
@@ -470,6 +555,7 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
             if (lane == 31) S.wsum[wid] = inc;
             if (tid == 0) S.out[0] = carry;
             __syncthreads();
+            SE_CLK(5);
             uint32_t pos = carrybits + inc - mylen, band_bits = 0;
 #pragma unroll
             for (int q = 0; q < SE_WARPS; q++) {
@@ -484,35 +570,31 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
                 // one window: my codes are concatenated in registers and leave as whole words; the first and the last
                 // word of my range are shared with my neighbours (atomicOr), the words between are mine alone
                 uint32_t wi = pos >> 5, sh = pos & 31u, wv = 0;
-                bool shared = true;
-                auto flush = [&](uint32_t wgt, uint32_t v) {
-                    if (shared) { if (v) atomicOr(&S.out[wgt], v); shared = false; }
-                    else S.out[wgt] = v;
-                };
+                bool shared = true;   // the word being filled may hold bits of another thread (or of my own long code)
 #pragma unroll
                 for (int q = 0; q < SE_PPT; q++) {
                     const uint32_t len = rec_len(r[q]);
-                    if (len == 0) continue;
-                    if (len <= (uint32_t)REC_SHORT_MAX) {
-                        const uint32_t left = (r[q] & 0x3fffffu) << (32u - len);
-                        wv |= left >> sh;
-                        if (sh + len >= 32u) {
-                            flush(wi, wv);
-                            wi++;
-                            wv = sh + len > 32u ? left << (32u - sh) : 0u;
-                            sh = sh + len - 32u;
-                        } else {
-                            sh += len;
-                        }
-                    } else {
+                    if (len > (uint32_t)REC_SHORT_MAX) {
                         // long unary run: my partial word first, then field by field
                         if (wv) atomicOr(&S.out[wi], wv);
                         const uint32_t at = (wi << 5) + sh;
-                        emit_fields(r[q], at, [&](uint32_t off, uint32_t val, uint32_t nb) { put_bits_smem(S.out, off, val, (int)nb); });
+                        pack_long(S.out, r[q], at);
                         const uint32_t np2 = at + len;
                         wi = np2 >> 5; sh = np2 & 31u; wv = 0;
                         shared = true;
+                        continue;
                     }
+                    const uint32_t left = ((r[q] & 0x3fffffu) << 1) << (31u - len);   // code word, MSB aligned (nothing for len 0)
+                    wv |= left >> sh;
+                    const uint32_t nsh = sh + len;
+                    if (nsh >= 32u) {                                                  // the word is full: sh >= 10 here
+                        if (shared) atomicOr(&S.out[wi], wv);
+                        else S.out[wi] = wv;
+                        shared = false;
+                        wi++;
+                        wv = left << (32u - sh);
+                    }
+                    sh = nsh & 31u;
                 }
                 if (wv) atomicOr(&S.out[wi], wv);
                 __syncthreads();
@@ -553,6 +635,7 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
             }
             carrybits = win_bits & 31u;
             total_bits += band_bits;
+            SE_CLK(6);
         }
         // byte_align + flush (compression.rs:279-280): the last partial word leaves zero padded
         if (tid == 0) {
@@ -564,6 +647,9 @@ __global__ void __launch_bounds__(SE_THREADS, 3) k_stream_encode(StreamArgs a) {
             a.flags[p] = ovf;
         }
     }
+    if (clk)
+        for (int i = 0; i < 8; i++) atomicAdd(a.clocks + i, (unsigned long long)tclk[i]);
+#undef SE_CLK
 }
 
 // offsets of a sub-batch: exclusive scan of the image sizes on top of a running total kept on the device
@@ -667,6 +753,7 @@ int stream_plan(felics_ctx *ctx, const felics_header &hdr, bool vec16, StreamPla
     a.halo_cap = (uint32_t)align_up(pl.w, 16);
     a.vec16 = vec16 && pl.w % 16 == 0 ? 1u : 0u;
     a.slot_bytes = pl.slot_bytes;
+    a.dbg = ctx->stream_dbg;
     pl.smem = ((sizeof(SeSmem) + 15) & ~(size_t)15) + 2 * (size_t)(a.halo_cap + SE_BAND + 16);
     if (!ctx->stream_attr_done) {
         FELICS_CUDA_TRY(cudaFuncSetAttribute(k_stream_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -684,13 +771,14 @@ int stream_plan(felics_ctx *ctx, const felics_header &hdr, bool vec16, StreamPla
 // encode `ni` images, scan their sizes on top of *d_running, copy the streams to `target` (which starts at absolute offset
 // *base_ptr of the whole batch's stream, nullptr = 0)
 int stream_launch(felics_ctx *ctx, StreamPlan &pl, size_t ni, const uint8_t *d_pixels, uint32_t *d_sizes, uint32_t *d_flags, uint64_t *d_off,
-                  uint32_t *d_ticket, uint64_t *d_running, uint8_t *d_temp, uint8_t *target, const uint64_t *base_ptr, uint64_t target_cap) {
+                  uint32_t *d_ticket, uint64_t *d_running, uint8_t *d_temp, uint8_t *target, const uint64_t *base_ptr, uint64_t target_cap,
+                  unsigned long long *d_clocks) {
     cudaStream_t st = ctx->stream;
     {
         StageScope s(ctx, ST_STREAM);
         FELICS_CUDA_TRY(cudaMemsetAsync(d_ticket, 0, sizeof(uint32_t), st));
         StreamArgs a = pl.a;
-        a.pixels = d_pixels; a.temp = d_temp; a.sizes = d_sizes; a.flags = d_flags; a.ticket = d_ticket; a.nplanes = (uint32_t)ni;
+        a.pixels = d_pixels; a.temp = d_temp; a.sizes = d_sizes; a.flags = d_flags; a.ticket = d_ticket; a.nplanes = (uint32_t)ni; a.clocks = d_clocks;
         const unsigned blocks = (unsigned)std::min<size_t>(ni, (size_t)ctx->sm_count * pl.per_sm);
         k_stream_encode<<<blocks, SE_THREADS, pl.smem, st>>>(a);
         s.launched();
@@ -708,6 +796,7 @@ int stream_launch(felics_ctx *ctx, StreamPlan &pl, size_t ni, const uint8_t *d_p
 struct StreamScratch {
     uint32_t *sizes, *flags, *ticket;
     uint64_t *off, *running;
+    unsigned long long *clocks;
     uint8_t *temp;
 };
 
@@ -715,12 +804,12 @@ int stream_scratch(felics_ctx *ctx, size_t n, size_t temp_bytes, StreamScratch &
     size_t off = 0;
     auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t at = off; off += bytes; return at; };
     const size_t o_sizes = take(n * sizeof(uint32_t)), o_flags = take(n * sizeof(uint32_t)), o_off = take((n + 1) * sizeof(uint64_t));
-    const size_t o_ctr = take(64), o_temp = take(temp_bytes);
+    const size_t o_ctr = take(256), o_temp = take(temp_bytes);
     int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off);
     if (rc) return rc;
     uint8_t *b = (uint8_t *)ctx->scratch;
     sc.sizes = (uint32_t *)(b + o_sizes); sc.flags = (uint32_t *)(b + o_flags); sc.off = (uint64_t *)(b + o_off);
-    sc.ticket = (uint32_t *)(b + o_ctr); sc.running = (uint64_t *)(b + o_ctr + 16); sc.temp = b + o_temp;
+    sc.ticket = (uint32_t *)(b + o_ctr); sc.running = (uint64_t *)(b + o_ctr + 16); sc.clocks = (unsigned long long *)(b + o_ctr + 64); sc.temp = b + o_temp;
     return FELICS_OK;
 }
 
@@ -737,11 +826,11 @@ int stream_encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, 
     const size_t sub_max = std::max<size_t>(1, std::min<size_t>(n, ((size_t)4 << 30) / pl.slot_bytes));
     StreamScratch sc;
     if ((rc = stream_scratch(ctx, n, sub_max * pl.slot_bytes, sc))) return rc;
-    FELICS_CUDA_TRY(cudaMemsetAsync(sc.ticket, 0, 64, st));
+    FELICS_CUDA_TRY(cudaMemsetAsync(sc.ticket, 0, 256, st));
     for (size_t first = 0; first < n; first += sub_max) {
         const size_t ni = std::min(sub_max, n - first);
         rc = stream_launch(ctx, pl, ni, (const uint8_t *)d_pixels + first * (size_t)pl.npix, sc.sizes + first, sc.flags + first, sc.off + first, sc.ticket,
-                           sc.running, sc.temp, d_arena, nullptr, arena_cap);
+                           sc.running, sc.temp, d_arena, nullptr, arena_cap, sc.clocks);
         if (rc) return rc;
     }
     // one read-back at the end: offsets and overflow flags
@@ -754,6 +843,15 @@ int stream_encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, 
     FELICS_CUDA_TRY(cudaStreamSynchronize(st));
     FELICS_CUDA_TRY(cudaGetLastError());
     std::memcpy(offsets_host, h_off, (n + 1) * sizeof(uint64_t));
+    if (ctx->stream_dbg & 8u) {   // timing experiment: share of every phase in the blocks' cycles
+        unsigned long long hc[8];
+        if (cudaMemcpy(hc, sc.clocks, sizeof(hc), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double tot = 0;
+            for (int i = 0; i < 7; i++) tot += (double)hc[i];
+            fprintf(stderr, "stream phases (%% of block cycles): load-wait %.1f group %.1f chains %.1f walk %.1f walk-barrier %.1f code+scan %.1f pack+flush %.1f\n", 100 * hc[0] / tot,
+                    100 * hc[1] / tot, 100 * hc[2] / tot, 100 * hc[3] / tot, 100 * hc[4] / tot, 100 * hc[5] / tot, 100 * hc[6] / tot);
+        }
+    }
     if (offsets_host[n] > arena_cap) {
         set_error("output capacity %zu too small (need %llu)", arena_cap, (unsigned long long)offsets_host[n]);
         profile_collect(ctx);
@@ -830,7 +928,7 @@ int stream_encode_batch_host(felics_ctx *ctx, size_t n, const void *h_pixels, co
             return fail(FELICS_ERR_CUDA);                                                                              \
         }                                                                                                              \
     } while (0)
-    SE_TRY(cudaMemsetAsync(sc.ticket, 0, 64, st));
+    SE_TRY(cudaMemsetAsync(sc.ticket, 0, 256, st));
     SE_TRY(cudaEventRecord(ctx->ev_done[0], st));   // the copy streams start after whatever the caller queued on the context's stream
     SE_TRY(cudaEventRecord(ctx->ev_done[1], st));
     SE_TRY(cudaEventRecord(ctx->ev_out[0], st));
@@ -865,7 +963,7 @@ int stream_encode_batch_host(felics_ctx *ctx, size_t n, const void *h_pixels, co
         SE_TRY(cudaStreamWaitEvent(st, ctx->ev_in[slot], 0));
         SE_TRY(cudaStreamWaitEvent(st, ctx->ev_out[slot], 0));   // the copy-out that last read this slot's streams
         rc = stream_launch(ctx, pl, ni, (const uint8_t *)ctx->stage_in[slot], sc.sizes + first, sc.flags + first, sc.off + first, sc.ticket, sc.running,
-                           sc.temp, (uint8_t *)ctx->stage_out[slot], sc.off + first, sub * pl.slot_bytes);
+                           sc.temp, (uint8_t *)ctx->stage_out[slot], sc.off + first, sub * pl.slot_bytes, sc.clocks);
         if (rc) return fail(rc);
         SE_TRY(cudaEventRecord(ctx->ev_done[slot], st));
         SE_TRY(cudaEventRecord(ctx->ev_pack[slot], st));

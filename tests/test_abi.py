@@ -13,18 +13,33 @@ import felics_b200
 from conftest import ROOT
 
 
-def declared_functions():
-    text = (ROOT / "include" / "felics_b200.h").read_text()
+def declared_functions(header="felics_b200.h"):
+    text = (ROOT / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(felics_[a-z0-9_]+)\s*\(", text)))
+
+
+def exported_functions():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", str(ROOT / "felics_b200" / "libfelics_b200.so")], check=True, capture_output=True, text=True).stdout
+    return sorted({line.split()[-1] for line in out.splitlines() if " T " in line and line.split()[-1].startswith("felics_")})
 
 
 def test_library_exports_every_declared_symbol():
     lib = felics_b200.load_library()
     names = declared_functions()
     assert len(names) >= 20
-    for name in names:
-        assert hasattr(lib, name), f"{name} declared in include/felics_b200.h but not exported"
+    for name in names + declared_functions("felics_b200_debug.h"):
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+
+
+def test_every_exported_symbol_is_declared():
+    # the other direction: nothing leaves the library that a header does not declare; the drop-in boundary is
+    # felics_b200.h, test and bench aids live in felics_b200_debug.h
+    api, dbg = set(declared_functions()), set(declared_functions("felics_b200_debug.h"))
+    assert not (api & dbg) and all(n.startswith("felics_debug_") for n in dbg)
+    exported = set(exported_functions())
+    assert exported == api | dbg, f"undeclared exports: {sorted(exported - api - dbg)}; missing: {sorted((api | dbg) - exported)}"
 
 
 def test_header_roundtrip_and_layout():  # format.rs:51-61
