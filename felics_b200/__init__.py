@@ -107,6 +107,8 @@ def load_library() -> C.CDLL:
     L.felics_compress_batch_device.argtypes = [vp, sz, vp, hp, vp, sz, u64p]
     L.felics_decompress_batch.argtypes = [vp, sz, vp, u64p, hp, vp, C.POINTER(C.c_int)]
     L.felics_decompress_batch_device.argtypes = [vp, sz, vp, u64p, hp, vp, C.POINTER(C.c_int)]
+    L.felics_compress_batch_v.argtypes = [vp, sz, C.POINTER(vp), hp, vp, sz, u64p]
+    L.felics_decompress_batch_v.argtypes = [vp, sz, vp, u64p, C.POINTER(vp), C.POINTER(sz), hp, C.POINTER(C.c_int)]
     L.felics_sidecar_build.argtypes = [vp, C.c_uint32, vp, sz, C.POINTER(sz)]
     L.felics_decompress_sidecar.argtypes = [vp, vp, sz, vp, sz, vp, sz, hp]
     L.felics_profile_enable.argtypes = [vp, C.c_int]
@@ -314,6 +316,48 @@ class Codec:
         if rc and (rc in (-9, -10, -12) or rc not in status[:n]):   # a failure of the whole call, not of one image
             _raise(rc)
         return out, status[:n]
+
+    # ---- batches of images of different shapes / pixel types (felics_compress_batch_v) ---------
+    def compress_many(self, images: Sequence[np.ndarray]):
+        """images: any mix of HxW / HxWx3, uint8 / uint16.  Returns (arena bytes as np.uint8, offsets[n+1])."""
+        images = [np.ascontiguousarray(im) for im in images]
+        n = len(images)
+        hdrs = (_CHeader * max(n, 1))(*[_c_header(_header_of(im)) for im in images])
+        ptrs = (C.c_void_p * max(n, 1))(*[im.ctypes.data for im in images])
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        cap = sum(im.nbytes for im in images) * 3 // 4 + 128 * n + 4096
+        for _ in range(2):
+            arena = np.empty(cap, dtype=np.uint8)
+            rc = self._lib.felics_compress_batch_v(self._h, n, ptrs, hdrs, arena.ctypes.data, cap, offsets.ctypes.data_as(C.POINTER(C.c_uint64)))
+            if rc == -8:
+                cap = int(offsets[n]) + 64
+                continue
+            if rc:
+                _raise(rc)
+            return arena[: int(offsets[n])], offsets
+        _raise(rc)
+
+    def decompress_many(self, arena: np.ndarray, offsets: Sequence[int]):
+        """Returns (list of images or None, status[n]); shapes and types come from the files' own headers."""
+        arena = np.ascontiguousarray(arena, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        outs, caps = [], []
+        for i in range(n):
+            try:
+                h = read_header(arena[int(offsets[i]):int(offsets[i + 1])].tobytes())
+                outs.append(np.zeros(_shape_of(h), dtype=_dtype_of(h)))
+            except DecompressionError:
+                outs.append(np.zeros(1, np.uint8))
+            caps.append(outs[-1].nbytes)
+        ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data for o in outs])
+        capv = (C.c_size_t * max(n, 1))(*caps)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        rc = self._lib.felics_decompress_batch_v(self._h, n, arena.ctypes.data, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), ptrs, capv, None,
+                                                 status.ctypes.data_as(C.POINTER(C.c_int)))
+        if rc and (rc in (-9, -10, -12) or rc not in status[:n]):
+            _raise(rc)
+        return [o if status[i] == 0 else None for i, o in enumerate(outs)], status[:n]
 
     # ---- device-resident entry points (raw device pointers, e.g. torch tensors' data_ptr()) ----
     def set_stream(self, cuda_stream: int):

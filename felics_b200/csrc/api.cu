@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <map>
 #include <new>
+#include <utility>
+#include <vector>
 
 namespace felics {
 
@@ -313,6 +316,112 @@ int felics_decompress(felics_ctx *ctx, const uint8_t *fel, size_t len, void *pix
     uint64_t off[2] = {0, (uint64_t)len};
     int status = 0;
     return felics_decompress_batch(ctx, 1, fel, off, &hdr, pixels_out, &status);
+}
+
+// ---- batches of mixed shapes: images that share a header travel through the device together -------------------------
+namespace {
+struct HeaderKey {
+    uint8_t color, depth;
+    uint32_t w, h;
+    bool operator<(const HeaderKey &o) const {
+        if (color != o.color) return color < o.color;
+        if (depth != o.depth) return depth < o.depth;
+        if (w != o.w) return w < o.w;
+        return h < o.h;
+    }
+};
+}  // namespace
+
+int felics_compress_batch_v(felics_ctx *ctx, size_t n, const void *const *pixels, const felics_header *hdrs, uint8_t *arena, size_t arena_cap,
+                            uint64_t *offsets) {
+    if (!ctx || !offsets || (n && (!pixels || !hdrs || !arena))) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    offsets[0] = 0;
+    if (n == 0) return FELICS_OK;
+    std::map<HeaderKey, std::vector<size_t>> groups;
+    for (size_t i = 0; i < n; i++) {
+        if ((rc = check_header(&hdrs[i]))) return rc;
+        if (!pixels[i] && felics_pixel_bytes(&hdrs[i])) { set_error("null pixels for image %zu", i); return FELICS_ERR_INVALID_ARGUMENT; }
+        groups[HeaderKey{hdrs[i].color_type, hdrs[i].pixel_depth, hdrs[i].width, hdrs[i].height}].push_back(i);
+    }
+    // every group is encoded as one batch of equally shaped images into a host buffer of its own; the streams are put in
+    // image order once all sizes are known
+    std::vector<uint64_t> sizes(n, 0);
+    std::vector<std::pair<const std::vector<size_t> *, std::vector<uint8_t>>> done;
+    std::vector<std::vector<uint64_t>> goffs;
+    done.reserve(groups.size());
+    for (auto &kv : groups) {
+        const std::vector<size_t> &idx = kv.second;
+        const felics_header hdr = hdrs[idx[0]];
+        const size_t per = felics_pixel_bytes(&hdr), m = idx.size();
+        std::vector<uint8_t> in(per * m + 16);
+        for (size_t j = 0; j < m; j++)
+            if (per) memcpy(in.data() + j * per, pixels[idx[j]], per);
+        std::vector<uint64_t> off(m + 1, 0);
+        std::vector<uint8_t> out(per * m / 2 + 64 * m + 4096);
+        rc = felics_compress_batch(ctx, m, in.data(), &hdr, out.data(), out.size(), off.data());
+        if (rc == FELICS_ERR_BUFFER_TOO_SMALL) {
+            out.resize((size_t)off[m] + 64);
+            rc = felics_compress_batch(ctx, m, in.data(), &hdr, out.data(), out.size(), off.data());
+        }
+        if (rc) return rc;
+        for (size_t j = 0; j < m; j++) sizes[idx[j]] = off[j + 1] - off[j];
+        done.emplace_back(&idx, std::move(out));
+        goffs.push_back(std::move(off));
+    }
+    for (size_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + sizes[i];
+    if (offsets[n] > arena_cap) {
+        set_error("output capacity %zu too small (need %llu)", arena_cap, (unsigned long long)offsets[n]);
+        return FELICS_ERR_BUFFER_TOO_SMALL;
+    }
+    for (size_t g = 0; g < done.size(); g++) {
+        const std::vector<size_t> &idx = *done[g].first;
+        for (size_t j = 0; j < idx.size(); j++) memcpy(arena + offsets[idx[j]], done[g].second.data() + goffs[g][j], (size_t)sizes[idx[j]]);
+    }
+    return FELICS_OK;
+}
+
+int felics_decompress_batch_v(felics_ctx *ctx, size_t n, const uint8_t *arena, const uint64_t *offsets, void *const *pixels_out, const size_t *caps,
+                              felics_header *hdrs_out, int *status) {
+    if (!ctx || !offsets || !status || (n && (!arena || !pixels_out || !caps))) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    if (n == 0) return FELICS_OK;
+    if ((rc = check_offsets(n, offsets))) return rc;
+    std::map<HeaderKey, std::vector<size_t>> groups;
+    for (size_t i = 0; i < n; i++) {
+        felics_header h;
+        status[i] = felics_read_header(arena + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), &h);   // read_header's own errors (format.rs:63-84)
+        if (status[i]) continue;
+        if (hdrs_out) hdrs_out[i] = h;
+        const uint64_t npix = (uint64_t)h.width * h.height;
+        if (npix > 0xffffffffull) { status[i] = FELICS_ERR_INVALID_DIMENSIONS; continue; }   // checked_mul (compression.rs:176-180)
+        if (felics_pixel_bytes(&h) > caps[i]) { status[i] = FELICS_ERR_BUFFER_TOO_SMALL; continue; }
+        groups[HeaderKey{h.color_type, h.pixel_depth, h.width, h.height}].push_back(i);
+    }
+    for (auto &kv : groups) {
+        const std::vector<size_t> &idx = kv.second;
+        felics_header hdr;
+        hdr.color_type = kv.first.color; hdr.pixel_depth = kv.first.depth; hdr.width = kv.first.w; hdr.height = kv.first.h;
+        const size_t per = felics_pixel_bytes(&hdr), m = idx.size();
+        std::vector<uint64_t> off(m + 1, 0);
+        for (size_t j = 0; j < m; j++) off[j + 1] = off[j] + (offsets[idx[j] + 1] - offsets[idx[j]]);
+        std::vector<uint8_t> in((size_t)off[m] + 16), out(per * m + 16);
+        for (size_t j = 0; j < m; j++) memcpy(in.data() + off[j], arena + offsets[idx[j]], (size_t)(off[j + 1] - off[j]));
+        std::vector<int> st(m, 0);
+        rc = felics_decompress_batch(ctx, m, in.data(), off.data(), &hdr, out.data(), st.data());
+        bool per_image = false;
+        for (size_t j = 0; j < m; j++) per_image |= st[j] == rc;
+        if (rc && !per_image) return rc;   // a failure of the call, not of one file
+        for (size_t j = 0; j < m; j++) {
+            status[idx[j]] = st[j];
+            if (st[j] == FELICS_OK && per) memcpy(pixels_out[idx[j]], out.data() + j * per, per);
+        }
+    }
+    for (size_t i = 0; i < n; i++)
+        if (status[i]) return status[i];
+    return FELICS_OK;
 }
 
 int felics_sidecar_build(felics_ctx *ctx, uint32_t band_rows, uint8_t *sidecar_out, size_t cap, size_t *out_len) {

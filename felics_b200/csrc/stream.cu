@@ -126,9 +126,11 @@ __device__ __forceinline__ uint32_t make_info(int p, int v1, int v2) {
     const uint32_t top = (~(uint32_t)(below & above) & 0x80000000u) | ((~(uint32_t)above >> 1) & 0x40000000u);   // [31] out of range, [30] above
     return top | (val << 21) | ((uint32_t)(h - l) << 12);
 }
-// pixels of the first row and the first column (misc.rs:6-24); pb = first pixel of the band, j = offset in the band, i = index in the plane
-__device__ __noinline__ uint32_t classify_edge(const uint8_t *pb, int j, uint32_t i, uint32_t x, uint32_t y, int w, const uint8_t *plane) {
-    if (i < 2) return SE_INFO_NONE;
+// any pixel (misc.rs:6-24): steps that touch a row start, the first row or the end of the image; pb = first pixel of the band,
+// j = offset in the band, i = index in the plane
+__device__ __noinline__ uint32_t classify_any(const uint8_t *pb, int j, uint32_t i, int w, uint32_t npix, const uint8_t *plane) {
+    if (i < 2 || i >= npix) return SE_INFO_NONE;
+    const uint32_t y = i / (uint32_t)w, x = i - y * (uint32_t)w;
     const int p = pb[j];
     int v1, v2;
     if (x > 0 && y > 0) { v1 = pb[j - 1]; v2 = pb[j - w]; }
@@ -413,16 +415,16 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 __syncwarp();
                 const uint32_t wp0 = wid * SE_WPIX;
                 {
-                    const uint32_t i0 = start + wp0 + lane;
-                    uint32_t y = i0 / a.w, x = i0 - y * a.w;
+                    // position of the step's first pixel: the same in every lane.  A step whose 32 pixels lie inside one row,
+                    // none of them in the first column or the first row, takes left and up without any per-pixel test
+                    uint32_t ys = (start + wp0) / a.w, xs = (start + wp0) - ys * a.w;
+                    const uint8_t *pj = pb + wp0 + lane;
+                    uint32_t *ij = &S.info[info_index(wp0 + lane)];          // info_index advances by 40 words per 32 pixels
 #pragma unroll 2
                     for (int s = 0; s < SE_WSTEPS; s++) {
-                        const uint32_t j = wp0 + 32u * s + lane;
-                        uint32_t wd = SE_INFO_NONE;
-                        if (j < cnt) {
-                            if (x > 0 && y > 0) wd = make_info(pb[j], pb[(int)j - 1], pb[(int)j - w]);
-                            else wd = classify_edge(pb, (int)j, start + j, x, y, w, plane);
-                        }
+                        uint32_t wd;
+                        if (ys >= 1 && xs >= 1 && xs + 32u <= a.w && wp0 + 32u * s + 32u <= cnt) wd = make_info(pj[0], pj[-1], pj[-w]);
+                        else wd = classify_any(pb, (int)(wp0 + 32u * s + lane), start + wp0 + 32u * s + lane, w, a.npix, plane);
                         const bool oor = wd >> 31;
                         const uint32_t act = __ballot_sync(0xffffffffu, oor);
                         if (act) {
@@ -437,9 +439,10 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                             }
                             __syncwarp();
                         }
-                        S.info[info_index(j)] = wd;
-                        x += 32;
-                        while (x >= a.w) { x -= a.w; y++; }
+                        *ij = wd;
+                        ij += 40; pj += 32;
+                        xs += 32;
+                        while (xs >= a.w) { xs -= a.w; ys++; }
                     }
                 }
                 // bases of the warp's segments: exclusive prefix of the counts, every segment padded to a multiple of four
@@ -461,14 +464,16 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                     c4[1] = make_uint4(((base + ex[4]) << 16) | n[4], ((base + ex[5]) << 16) | n[5], ((base + ex[6]) << 16) | n[6], ((base + ex[7]) << 16) | n[7]);
                 }
                 __syncwarp();
+                {
+                    uint32_t *iw = &S.info[info_index(wp0 + lane)];
 #pragma unroll 4
-                for (int s = 0; s < SE_WSTEPS; s++) {
-                    uint32_t *iw = &S.info[info_index(wp0 + 32u * s + lane)];
-                    const uint32_t wd = *iw;
-                    if (wd >> 31) {
-                        const uint32_t pos = (cntw[(wd >> 12) & 255u] >> 16) + (wd & 0xfffu);
-                        ecw[pos] = (uint8_t)((wd >> 21) & 511u);
-                        *iw = (wd & 0xffe00000u) | pos;
+                    for (int s = 0; s < SE_WSTEPS; s++, iw += 40) {
+                        const uint32_t wd = *iw;
+                        if (wd >> 31) {
+                            const uint32_t pos = (cntw[(wd >> 12) & 255u] >> 16) + (wd & 0xfffu);
+                            ecw[pos] = (uint8_t)((wd >> 21) & 511u);
+                            *iw = (wd & 0xffe00000u) | pos;
+                        }
                     }
                 }
             } else {
@@ -567,10 +572,9 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
 
             // ---- pack ---------------------------------------------------------------------------------------
             if (win_bits <= (uint32_t)SE_OUT_WORDS * 32u) {
-                // one window: my codes are concatenated in registers and leave as whole words; the first and the last
-                // word of my range are shared with my neighbours (atomicOr), the words between are mine alone
+                // one window: my codes are concatenated in registers and leave as whole words (atomicOr: the first and the last
+                // word of my range are shared with my neighbours; about two words per thread and band)
                 uint32_t wi = pos >> 5, sh = pos & 31u, wv = 0;
-                bool shared = true;   // the word being filled may hold bits of another thread (or of my own long code)
 #pragma unroll
                 for (int q = 0; q < SE_PPT; q++) {
                     const uint32_t len = rec_len(r[q]);
@@ -581,16 +585,13 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                         pack_long(S.out, r[q], at);
                         const uint32_t np2 = at + len;
                         wi = np2 >> 5; sh = np2 & 31u; wv = 0;
-                        shared = true;
                         continue;
                     }
                     const uint32_t left = ((r[q] & 0x3fffffu) << 1) << (31u - len);   // code word, MSB aligned (nothing for len 0)
                     wv |= left >> sh;
                     const uint32_t nsh = sh + len;
                     if (nsh >= 32u) {                                                  // the word is full: sh >= 10 here
-                        if (shared) atomicOr(&S.out[wi], wv);
-                        else S.out[wi] = wv;
-                        shared = false;
+                        atomicOr(&S.out[wi], wv);
                         wi++;
                         wv = left << (32u - sh);
                     }

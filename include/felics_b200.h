@@ -87,7 +87,8 @@ int felics_decompress(felics_ctx *ctx, const uint8_t *fel, size_t len,
                       void *pixels_out, size_t cap, felics_header *hdr_out);
 
 /* Same two calls with DEVICE-resident buffers (no host<->device copy of the
- * payload; used to time the kernels alone).  d_out needs 4-byte alignment. */
+ * payload; used to time the kernels alone).  d_out and d_fel need 4-byte alignment, and the decoder loads whole
+ * 32-bit words: the allocation behind d_fel must be readable up to the next multiple of four bytes after `len`. */
 int felics_compress_device(felics_ctx *ctx, const void *d_pixels, const felics_header *hdr,
                            uint8_t *d_out, size_t cap, size_t *out_len);
 int felics_decompress_device(felics_ctx *ctx, const uint8_t *d_fel, size_t len,
@@ -98,7 +99,8 @@ int felics_decompress_device(felics_ctx *ctx, const uint8_t *d_fel, size_t len,
  * reference, tests/compress.rs:15-35).  Image i's pixels start at
  * pixels + i*felics_pixel_bytes(hdr); its .fel occupies
  * arena[offsets[i] .. offsets[i+1]).  `offsets` has n+1 entries (host memory).
- * *_device variants take device pointers for pixels/arena. */
+ * *_device variants take device pointers for pixels/arena (the arena 4-byte aligned, except for batches of 8-bit gray
+ * images, which accept any alignment). */
 int felics_compress_batch(felics_ctx *ctx, size_t n, const void *pixels, const felics_header *hdr,
                           uint8_t *arena, size_t arena_cap, uint64_t *offsets);
 int felics_compress_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const felics_header *hdr,
@@ -111,6 +113,19 @@ int felics_decompress_batch(felics_ctx *ctx, size_t n, const uint8_t *arena, con
                             const felics_header *hdr, void *pixels_out, int *status);
 int felics_decompress_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const uint64_t *offsets,
                                    const felics_header *hdr, void *d_pixels_out, int *status);
+
+/* Batches of images of DIFFERENT shapes and pixel types (BASELINE.json configs[4]; the reference's own loop over the
+ * image suite compresses 146 differently sized files one after the other, tests/compress.rs:74-103): image i has header
+ * hdrs[i] and its pixels at pixels[i] (HOST memory); its .fel occupies arena[offsets[i] .. offsets[i+1]) (HOST memory,
+ * n+1 offsets).  Images that share a header are encoded together as one batch on the device; the streams are byte-identical
+ * to n separate felics_compress calls.  On FELICS_ERR_BUFFER_TOO_SMALL offsets[n] holds the size the arena needs. */
+int felics_compress_batch_v(felics_ctx *ctx, size_t n, const void *const *pixels, const felics_header *hdrs,
+                            uint8_t *arena, size_t arena_cap, uint64_t *offsets);
+/* The inverse: n .fel files of any shapes in one arena; image i is decoded into pixels_out[i], which holds caps[i] bytes.
+ * hdrs_out[i] receives the file's header whenever it parses; status[i] the per-image return code
+ * (FELICS_ERR_BUFFER_TOO_SMALL when caps[i] is too small); the call returns the first non-zero status. */
+int felics_decompress_batch_v(felics_ctx *ctx, size_t n, const uint8_t *arena, const uint64_t *offsets,
+                              void *const *pixels_out, const size_t *caps, felics_header *hdrs_out, int *status);
 
 /* ---- band sidecar (opt-in; NOT part of the reference .fel format) ----
  * A .fel file is one serial bit chain per plane (compression.rs:151-248), so one big image decodes on one warp.
