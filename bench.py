@@ -11,6 +11,8 @@ N = 1 holds all of it.  A step = one encode of the rank's whole shard; value = 6
 The per-image sizes are gathered over NCCL (sharding.gather_sizes) -- the only exchange -- and >= 256 sampled tiles per rank
 are compared with the CPU oracle.  `--workload image|rgb|gray16` select the single-image configs (configs[1], configs[2],
 SURVEY 8(f)1: independent replicas per GPU, weak scaling); the default run reports them as extra keys (`other_configs`).
+`--workload corpus` is configs[4]: the seven RGB images of the reference's bench/tiff_files (committed as pixels under
+tests/golden/), mirror-tiled to 2048^2 and 4096^2 and replicated to 512 images per GPU (4096 at 8 GPUs), two shapes per rank.
 
 value : whole-job encode MPixel/s with the input already resident in HBM (device entry point)
 e2e   : the same through the host-memory C ABI call (felics_compress_batch): H2D of the pixels from pinned host memory and
@@ -162,6 +164,9 @@ def workload_name(args):
         return "SURVEY 8(f)1: one synthetic 4096x4096 gray16 image (G-nat x 256, noise sigma 192, seed 2+rank) per GPU, encode"
     if args.workload == "image":
         return "configs[1]: one synthetic 8192x8192 gray8 image (G-nat, seed 2+rank) per GPU, encode"
+    if args.workload == "corpus":
+        return (f"configs[4]: the 7 RGB8 images of bench/tiff_files mirror-tiled to 2048x2048 and 4096x4096 (14 sources), replicated to "
+                f"{args.corpus_images} images per GPU ({args.corpus_images * args.gpus} in the job; 4096 at 8 GPUs), encode")
     return (f"configs[3]: batch of {args.tiles} synthetic 512x512 gray8 tiles (integer generator, seed 1), contiguous shards over the GPUs, encode")
 
 
@@ -216,6 +221,17 @@ def run_reference(args):
             t0 = time.perf_counter()
             cpu_tiles_rate(fo, imgs, threads)
             return time.perf_counter() - t0
+    elif args.workload == "corpus":
+        src = corpus_sources()
+        imgs = [im for side in CORPUS_SIDES for im in src[side]] * 2
+        threads = min(cores, len(imgs))
+        sample = f"the 14 source images twice per step, one image per thread at a time on {threads} threads"
+        px_per_step = sum(im.shape[0] * im.shape[1] for im in imgs)
+
+        def step():
+            t0 = time.perf_counter()
+            cpu_images_rate(fo, imgs, threads)
+            return time.perf_counter() - t0
     else:
         # single-image configs: the whole image (a single image is serial in the reference), one replica per GPU of our arm
         if args.workload == "gray16":
@@ -248,7 +264,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "strong" if args.workload == "tiles" else "weak",
+        "scaling": "strong" if args.workload == "tiles" else "weak",   # corpus and single images: per-GPU work is fixed
         "vs_baseline": None, "dtype": "u16" if args.workload == "gray16" else "u8", "data": "synthetic",
         "config": {"workload": workload_name(args)},
         "cpu_baseline": {"value": value, "unit": "MPixel/s", "cores": threads, "kind": "port", "sample": sample, **info,
@@ -658,6 +674,188 @@ def run_single(args, rig):
         "wall_s_timed_region": wall_dev,
     }
 
+# ---- configs[4]: the bench corpus, mirror-tiled and replicated ---------------------------------------
+CORPUS_SIDES = (2048, 4096)
+
+
+def corpus_sources():
+    """The 14 source images of configs[4]: tests/golden/bench_corpus.npz (the seven RGB files of the reference's
+    bench/tiff_files, committed as pixels by tests/golden/make_corpus.py) mirror-tiled to 2048^2 and 4096^2."""
+    from felics_b200.synth import mirror_tile
+    raw = dict(np.load(ROOT / "tests" / "golden" / "bench_corpus.npz"))
+    return {side: [mirror_tile(raw[n], side, side) for n in sorted(raw)] for side in CORPUS_SIDES}
+
+
+def corpus_plan(first, count):
+    """Images first .. first+count-1 of the job: image g is source g % 14 (g % 14 < 7: the 2048^2 version of corpus image
+    g % 7, otherwise its 4096^2 version).  Returns {side: [source index of every image of that side, in job order]}."""
+    plan = {side: [] for side in CORPUS_SIDES}
+    for g in range(first, first + count):
+        s = g % 14
+        plan[CORPUS_SIDES[s // 7]].append(s % 7)
+    return plan
+
+
+def cpu_images_rate(fo, images, threads):
+    """Oracle port, one image per thread at a time on `threads` host threads: MPixel/s over `images` (HxWx3)."""
+    threads = max(1, min(threads, len(images)))
+    todo = list(range(len(images)))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                if not todo:
+                    return
+                i = todo.pop()
+            fo.compress(images[i])
+    ts = [threading.Thread(target=work) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return sum(im.shape[0] * im.shape[1] for im in images) / (time.perf_counter() - t0) / 1e6
+
+
+def run_corpus(args, rig):
+    import ctypes as C
+    torch, fb, codec = rig.torch, rig.fb, rig.codec
+    from felics_b200 import sharding
+    from oracle import felics_oracle as fo
+
+    per_rank = args.corpus_images
+    total = per_rank * rig.world
+    first, count = sharding.shard_range(total, rig.rank, rig.world)
+    plan = corpus_plan(first, count)
+    src = corpus_sources()
+    groups = []   # one per shape: device batch, header, output arena
+    for side in CORPUS_SIDES:
+        idx = plan[side]
+        if not idx:
+            continue
+        d_src = torch.from_numpy(np.stack(src[side])).to(rig.dev)                       # (7, side, side, 3)
+        d_in = d_src[torch.tensor(idx, device=rig.dev)].contiguous()                    # replicated on the device
+        del d_src
+        hdr = fb.Header(fb.ColorType.Rgb, fb.PixelDepth.Eight, side, side)
+        cap = d_in.numel() * 3 // 4 + 4096 * len(idx)
+        groups.append({"side": side, "idx": idx, "d_in": d_in, "hdr": hdr, "cap": cap, "d_out": torch.empty(cap, dtype=torch.uint8, device=rig.dev)})
+    in_bytes = sum(g["d_in"].numel() for g in groups)
+    pixels = in_bytes // 3
+
+    def encode_device():
+        for g in groups:
+            g["offsets"] = codec.compress_batch_device(len(g["idx"]), g["d_in"].data_ptr(), g["hdr"], g["d_out"].data_ptr(), g["cap"])
+
+    sampler = ClockSampler(rig.local)
+    sampler.start()
+    for _ in range(max(args.warmup, 1)):
+        encode_device()
+    fel_bytes = sum(int(g["offsets"][-1]) for g in groups)
+    codec.profile(True)
+    rig.barrier()
+    sampler.mark()
+    t_wall0 = time.perf_counter()
+    ms_dev = rig.timed(encode_device, args.steps)      # every rank's input (>= 1 GiB) and output exceed the L2
+    wall_dev = time.perf_counter() - t_wall0
+    rig.barrier()
+    stages = codec.stage_times()
+    launches = codec.total_launches()
+    codec.profile(False)
+
+    sizes = np.concatenate([np.diff(g["offsets"].astype(np.int64)) for g in groups]) if groups else np.zeros(0, np.int64)
+    all_sizes = sharding.gather_sizes(sizes)
+    assert len(all_sizes) == total
+
+    # parity: the first replica of every distinct source on this rank against the oracle, bit-exact .fel bytes
+    mismatches = checked = 0
+    if args.verify:
+        for g in groups:
+            seen = set()
+            for j, s in enumerate(g["idx"]):
+                if s in seen:
+                    continue
+                seen.add(s)
+                got = g["d_out"][int(g["offsets"][j]):int(g["offsets"][j + 1])].cpu().numpy().tobytes()
+                mismatches += got != fo.compress(src[g["side"]][s])
+                checked += 1
+
+    decode = None
+    if args.decode:
+        dec_ms, lossless = 0.0, True
+        for g in groups:
+            d_pix = torch.empty_like(g["d_in"])
+            codec.profile(True)
+            status = codec.decompress_batch_device(len(g["idx"]), g["d_out"].data_ptr(), g["offsets"], g["hdr"], d_pix.data_ptr())
+            torch.cuda.synchronize(rig.dev)
+            dst = codec.stage_times()
+            codec.profile(False)
+            dec_ms += dst["decode"][0] + dst["unplane"][0]
+            lossless = lossless and (not status.any()) and bool(torch.equal(d_pix, g["d_in"]))
+            del d_pix
+        decode = (dec_ms, lossless)
+
+    # end to end through the mixed-shape host call (felics_compress_batch_v): the 14 sources twice, host pixels in, host arena out
+    e2e_imgs = [im for side in CORPUS_SIDES for im in src[side]] * 2
+    e2e_in = sum(im.nbytes for im in e2e_imgs)
+    hdrs = (fb._CHeader * len(e2e_imgs))(*[fb._c_header(fb._header_of(im)) for im in e2e_imgs])
+    pins = [torch.from_numpy(im).pin_memory() for im in e2e_imgs]
+    ptrs = (C.c_void_p * len(e2e_imgs))(*[p.data_ptr() for p in pins])
+    pin_out = rig.pinned(e2e_in * 3 // 4)
+    e2e_off = np.zeros(len(e2e_imgs) + 1, dtype=np.uint64)
+
+    def encode_host():
+        rc = rig.lib.felics_compress_batch_v(codec._h, len(e2e_imgs), ptrs, hdrs, C.c_void_p(pin_out.data_ptr()), pin_out.numel(),
+                                             e2e_off.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if rc:
+            raise RuntimeError(f"felics_compress_batch_v failed: {rc} {rig.lib.felics_last_error().decode()}")
+    encode_host()
+    rig.barrier()
+    e2e_steps = min(args.steps, 3)
+    ms_e2e = rig.timed(encode_host, e2e_steps)
+    rig.barrier()
+    clocks = sampler.stop()
+
+    tot_dev_ms = rig.reduce(sum(ms_dev), "max")
+    e2e_ms = rig.reduce(sum(ms_e2e) / len(ms_e2e), "max")
+    all_pixels = rig.reduce(float(pixels), "sum")
+    all_fel = rig.reduce(float(fel_bytes), "sum")
+    bad = rig.reduce(float(mismatches), "sum")
+    n_checked = rig.reduce(float(checked), "sum")
+    dec_ms = rig.reduce(decode[0], "max") if decode else None
+    dec_bad = rig.reduce(0.0 if (decode is None or decode[1]) else 1.0, "sum")
+    if rig.rank != 0:
+        return None
+    enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane") and v[1]}
+    roof = roofline_of(enc_stages, args.steps, in_bytes + fel_bytes, sum(ms_dev), "corpus")
+    info = cpu_info()
+    flat = [im for side in CORPUS_SIDES for im in src[side]]
+    one = cpu_images_rate(fo, flat[:3], 1)
+    allc = cpu_images_rate(fo, flat * 2, info["nproc"])
+    value = all_pixels * args.steps / (tot_dev_ms * 1e-3) / 1e6
+    e2e_px = sum(im.shape[0] * im.shape[1] for im in e2e_imgs) * rig.world
+    return {
+        "metric": "encode MPixel/s", "value": value, "unit": "MPixel/s", "n_gpus": rig.world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "bench/tiff_files pixels (committed), mirror-tiled and replicated",
+        "config": {"workload": workload_name(args), "images_total": total, "images_rank0": count, "input_bytes_rank0": in_bytes,
+                   "msample_per_s": 3 * value, "fel_bytes_total": int(all_fel), "bits_per_sample": 8.0 * all_fel / max(3 * all_pixels, 1),
+                   "sizes_gathered": int(len(all_sizes)), "l2": "not flushed: every rank's input and output exceed the 126 MB L2"},
+        "roofline": roof,
+        "cpu_baseline": {"value": allc, "unit": "MPixel/s", "cores": min(info["nproc"], 28), "kind": "port",
+                         "sample": "the 14 source images twice, one image per thread at a time on all host threads",
+                         "single_thread": {"value": one, "unit": "MPixel/s", "cores": 1, "sample": "the first three 2048x2048 sources"}, **info},
+        "e2e": {"value": e2e_px / (e2e_ms * 1e-3) / 1e6, "unit": "MPixel/s", "h2d_bytes_per_step": e2e_in, "d2h_bytes_per_step": int(e2e_off[-1]),
+                "ms_per_step": e2e_ms, "images_per_rank": len(e2e_imgs),
+                "note": "felics_compress_batch_v (mixed shapes) on pinned host images: the 14 sources twice per rank"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": dec_bad == 0.0, "files": total} if decode else None),
+        "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
+        "parity": (None if not args.verify else (f"bit-exact vs oracle on {int(n_checked)} images (every distinct source on every rank)" if bad == 0
+                                                 else f"MISMATCH vs oracle ({int(bad)} of {int(n_checked)})")),
+        "wall_s_timed_region": wall_dev,
+    }
+
 
 def run_ours(args):
     rig = Rig()
@@ -672,6 +870,8 @@ def run_ours(args):
                 except Exception as exc:   # informational only: never lose the main line
                     extra[key] = {"error": str(exc)}
             line["other_configs"] = extra
+    elif args.workload == "corpus":
+        line = run_corpus(args, rig)
     else:
         line = run_single(args, rig)
     if line is not None:
@@ -685,7 +885,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["tiles", "image", "rgb", "gray16"], default="tiles")
+    ap.add_argument("--workload", choices=["tiles", "image", "rgb", "gray16", "corpus"], default="tiles")
+    ap.add_argument("--corpus-images", type=int, default=512, help="images per GPU for --workload corpus (512 x 8 GPUs = the 4096 of configs[4])")
     ap.add_argument("--tiles", type=int, default=TOTAL_TILES, help="tiles in the whole batch (sharded over the GPUs) for --workload tiles")
     ap.add_argument("--parity-tiles", type=int, default=256, help="tiles per rank compared with the oracle")
     ap.add_argument("--no-verify", dest="verify", action="store_false", help="skip the oracle parity check of the timed output")

@@ -31,6 +31,7 @@
 #include "device_common.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -41,7 +42,7 @@ namespace {
 
 constexpr int SE_THREADS = 256;
 #ifndef SE_CTAS_PER_SM
-#define SE_CTAS_PER_SM 3
+#define SE_CTAS_PER_SM 4
 #endif
 constexpr int SE_WARPS = SE_THREADS / 32;
 constexpr int SE_PPT = 16;                                  // pixels per thread in the code / pack phase
@@ -66,17 +67,21 @@ __device__ __forceinline__ uint32_t info_index(uint32_t p) { return p + ((p >> 4
 struct SeSmem {
     uint32_t info[SE_INFO_WORDS];
     uint32_t wseg[SE_WARPS][SE_NCTX];   // per warp and context: count while ranking, then base << 16 | count inside the warp's region
-    uint32_t state[SE_NCTX][3];         // estimator row of a context: counts as u16 pairs (k0 | k1 << 16, k2 | k3 << 16, k4 | k5 << 16)
-    uint4 lut[SE_NCTX];                 // code costs of a residual under k = 0..5, times 8, as u16 pairs (nothing for SE_NULL_E)
-    uint32_t out[SE_OUT_WORDS + 4];     // the bit window
     uint32_t stepdone[SE_NCTX];         // steps of a chain walked so far in this band
+    uint32_t state[SE_NCTX][3];         // estimator row of a context: counts as u16 pairs (k0 | k1 << 16, k2 | k3 << 16, k4 | k5 << 16)
+    uint2 lut03[SE_NCTX];               // code costs of a residual under k = 0..3, times 8, as u16 pairs (nothing for SE_NULL_E)
+    uint32_t lut45[SE_NCTX];            // ... under k = 4, 5
     uint16_t longc[SE_NCTX];            // long chains of the band: context | steps << 8
     uint16_t shortlist[SE_NCTX];
     uint32_t roundcnt[40];              // chains that have a step s (a chain of a band has at most 34 steps)
     uint8_t ec[SE_WARPS][SE_WREG];      // residuals grouped by context, one region per warp; the walk overwrites them with k
     uint32_t wsum[SE_WARPS];
     uint32_t ntask, nlong, nshort, task, plane;
+    uint64_t bar[2];                    // one mbarrier per pixel buffer (TMA bulk loads)
 };
+// the bit window of the pack phase (SE_OUT_WORDS + 4 words) lies over wseg and stepdone: both are dead once the walk is over
+static_assert(sizeof(SeSmem::wseg) + sizeof(SeSmem::stepdone) >= (SE_OUT_WORDS + 4) * sizeof(uint32_t), "bit window does not fit");
+static_assert(offsetof(SeSmem, stepdone) == offsetof(SeSmem, wseg) + sizeof(SeSmem::wseg), "bit window must be contiguous");
 
 struct StreamArgs {
     const uint8_t *pixels;      // image p at pixels + p * npix
@@ -93,27 +98,51 @@ struct StreamArgs {
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async4(void *dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// pixels [start - hl, start + cnt) of the plane -> buf[halo_cap - hl ...): the band starts at buf + halo_cap
-__device__ __forceinline__ void load_band(uint8_t *buf, const StreamArgs &a, const uint8_t *plane, uint32_t start, uint32_t cnt) {
+// TMA bulk copy (cp.async.bulk, 1-D) completing on an mbarrier: one thread moves a whole band
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// pixels [start - hl, start + cnt) of the plane -> buf[halo_cap - hl ...): the band starts at buf + halo_cap.  Aligned images
+// (vec16: base, width and pixel count multiples of 16) travel as one TMA bulk copy issued by thread 0 that completes on `bar`;
+// the others as 4-byte cp.async copies by all threads
+__device__ __forceinline__ void load_band(uint8_t *buf, const StreamArgs &a, const uint8_t *plane, uint32_t start, uint32_t cnt, uint64_t *bar) {
     const uint32_t hl = min(a.w, start);
     const uint32_t total = hl + cnt;
     const uint8_t *src = plane + start - hl;
     uint8_t *dst = buf + a.halo_cap - hl;
     if (a.vec16) {
-        for (uint32_t o = 16u * threadIdx.x; o < total; o += 16u * SE_THREADS) cp_async16(dst + o, src + o);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, total);
+            bulk_load(dst, src, total, bar);
+        }
     } else {
         for (uint32_t o = 4u * threadIdx.x; o < total; o += 4u * SE_THREADS) cp_async4(dst + o, src + o);
+        cp_async_commit();
     }
-    cp_async_commit();
 }
 
 // compression.rs:118-145 for one pixel given its two neighbours.  At most one of L-P-1 and P-H-1 is non-negative:
@@ -153,9 +182,10 @@ __device__ __forceinline__ void store_state(uint32_t *row, const uint32_t (&v)[N
     row[0] = (v[0] >> 3) | ((v[1] >> 3) << 16); row[1] = (v[2] >> 3) | ((v[3] >> 3) << 16); row[2] = (v[4] >> 3) | ((v[5] >> 3) << 16);
 }
 // the six code costs (e >> k) + 1 + k of a residual (rice_coding.rs:56-58), times 8, from the table
-__device__ __forceinline__ void cost_keys(const uint4 *lut, uint32_t e, uint32_t (&c)[NK]) {
-    const uint4 t = lut[e];
-    c[0] = t.x & 0xffffu; c[1] = t.x >> 16; c[2] = t.y & 0xffffu; c[3] = t.y >> 16; c[4] = t.z & 0xffffu; c[5] = t.z >> 16;
+__device__ __forceinline__ void cost_keys(const SeSmem &S, uint32_t e, uint32_t (&c)[NK]) {
+    const uint2 t = S.lut03[e];
+    const uint32_t u = S.lut45[e];
+    c[0] = t.x & 0xffffu; c[1] = t.x >> 16; c[2] = t.y & 0xffffu; c[3] = t.y >> 16; c[4] = u & 0xffffu; c[5] = u >> 16;
 }
 __device__ __forceinline__ uint32_t min6(const uint32_t (&v)[NK]) { return min(min(min(v[0], v[1]), min(v[2], v[3])), min(v[4], v[5])); }
 __device__ __forceinline__ void halve_keys(uint32_t (&v)[NK]) {              // parameter_selection.rs:58-63
@@ -177,7 +207,7 @@ __device__ __forceinline__ void serial_walk(SeSmem &S, uint32_t c) {
             const uint32_t e = seg[i];
             seg[i] = (uint8_t)(5u - (m & 7u));
             uint32_t c6[NK];
-            cost_keys(S.lut, e, c6);
+            cost_keys(S, e, c6);
 #pragma unroll
             for (int k = 0; k < NK; k++) st[k] += c6[k];
             m = min6(st);
@@ -216,7 +246,7 @@ __device__ __forceinline__ void coop_step(SeSmem &S, uint32_t c, uint32_t step, 
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         uint32_t c6[NK];
-        cost_keys(S.lut, (word >> (8 * j)) & 255u, c6);
+        cost_keys(S, (word >> (8 * j)) & 255u, c6);
 #pragma unroll
         for (int k = 0; k < NK; k++) P[j][k] = j ? P[j - 1][k] + c6[k] : c6[k];
     }
@@ -348,6 +378,38 @@ __device__ __noinline__ void pack_long(uint32_t *out, uint32_t r, uint32_t at) {
     emit_fields(r, at, [&](uint32_t off, uint32_t val, uint32_t nb) { put_bits_smem(out, off, val, (int)nb); });
 }
 
+// A band of more than SE_OUT_WORDS * 32 bits (over 16 bits per pixel): the band leaves through several windows, every code
+// clipped to the window.  Called by the whole block; `recs` = the caller's SE_PPT records, `pos` = bit offset of its first one.
+__device__ __noinline__ void pack_windows(uint32_t *out, const uint32_t *recs, uint32_t pos, uint32_t win_bits, uint32_t *slot, uint32_t slot_words,
+                                          uint32_t &wpos, uint32_t &carry, uint32_t &ovf) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t wbits = (uint32_t)SE_OUT_WORDS * 32u;
+    for (uint32_t w0 = 0; w0 < win_bits; w0 += wbits) {
+        const uint32_t w1 = w0 + wbits;
+        if (w0) {
+            __syncthreads();
+            for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) out[i] = 0u;
+            __syncthreads();
+        }
+        uint32_t off = pos;
+#pragma unroll 1
+        for (int q = 0; q < SE_PPT; q++) {
+            const uint32_t rq = recs[q], len = rec_len(rq);
+            if (len && off < w1 && off + len > w0)
+                emit_fields(rq, off, [&](uint32_t o2, uint32_t val, uint32_t nb) { put_clipped(out, o2, val, nb, w0, w1); });
+            off += len;
+        }
+        __syncthreads();
+        const uint32_t nfull = w1 <= win_bits ? (uint32_t)SE_OUT_WORDS : (win_bits - w0) >> 5;
+        for (uint32_t j = tid; j < nfull; j += SE_THREADS) {
+            if (wpos + j < slot_words) slot[wpos + j] = bswap32(out[j]);
+        }
+        if (wpos + nfull >= slot_words) ovf = 1;
+        carry = w1 <= win_bits ? 0u : out[nfull];
+        wpos += nfull;
+    }
+}
+
 __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(StreamArgs a) {
     extern __shared__ __align__(16) unsigned char se_smem[];
     SeSmem &S = *reinterpret_cast<SeSmem *>(se_smem);
@@ -355,6 +417,7 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
     const uint32_t buf_bytes = a.halo_cap + SE_BAND + 16u;
     uint8_t *const pixbuf0 = se_smem + ((sizeof(SeSmem) + 15) & ~(size_t)15);   // two buffers of buf_bytes
     const uint32_t lt = (1u << lane) - 1u;
+    uint32_t *const out = &S.wseg[0][0];   // the bit window (see SeSmem)
     const uint32_t slot_words = (uint32_t)(a.slot_bytes >> 2);
     const int w = (int)a.w;
     long long tclk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
@@ -366,8 +429,16 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
         uint32_t c[NK];
 #pragma unroll
         for (int k = 0; k < NK; k++) c[k] = e == SE_NULL_E ? 0u : ((e >> k) + 1u + (uint32_t)k) << 3;
-        S.lut[e] = make_uint4(c[0] | (c[1] << 16), c[2] | (c[3] << 16), c[4] | (c[5] << 16), 0u);
+        S.lut03[e] = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
+        S.lut45[e] = c[4] | (c[5] << 16);
     }
+
+    if (tid == 0) {
+        mbar_init(&S.bar[0], 1);
+        mbar_init(&S.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t parity = 0;   // bit i: phase of S.bar[i] the next wait is for
 
     for (;;) {
         __syncthreads();
@@ -392,15 +463,21 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
         uint64_t total_bits = 176;
 
         const uint32_t nbands = (a.npix + SE_BAND - 1) / SE_BAND;
-        load_band(pixbuf0, a, plane, 0, min((uint32_t)SE_BAND, a.npix));
+        load_band(pixbuf0, a, plane, 0, min((uint32_t)SE_BAND, a.npix), &S.bar[0]);
         for (uint32_t b = 0; b < nbands; b++) {
             const uint32_t start = b * SE_BAND, cnt = min((uint32_t)SE_BAND, a.npix - start);
             const uint8_t *pb = pixbuf0 + (b & 1u) * buf_bytes + a.halo_cap;
             if (clk) tlast = clock64();
-            cp_async_wait_all();
+            if (a.vec16) {
+                mbar_wait(&S.bar[b & 1u], (parity >> (b & 1u)) & 1u);
+                parity ^= 1u << (b & 1u);
+            } else {
+                cp_async_wait_all();
+            }
             __syncthreads();
             SE_CLK(0);
-            if (b + 1 < nbands) load_band(pixbuf0 + ((b + 1) & 1u) * buf_bytes, a, plane, start + SE_BAND, min((uint32_t)SE_BAND, a.npix - start - SE_BAND));
+            if (b + 1 < nbands)
+                load_band(pixbuf0 + ((b + 1) & 1u) * buf_bytes, a, plane, start + SE_BAND, min((uint32_t)SE_BAND, a.npix - start - SE_BAND), &S.bar[(b + 1) & 1u]);
             if (tid == 0) { S.ntask = 0; S.nlong = 0; S.nshort = 0; S.task = 0; }
             if (tid < 40) S.roundcnt[tid] = 0u;
 
@@ -415,34 +492,39 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 __syncwarp();
                 const uint32_t wp0 = wid * SE_WPIX;
                 {
-                    // position of the step's first pixel: the same in every lane.  A step whose 32 pixels lie inside one row,
-                    // none of them in the first column or the first row, takes left and up without any per-pixel test
-                    uint32_t ys = (start + wp0) / a.w, xs = (start + wp0) - ys * a.w;
+                    // position of the step's first pixel: the same in every lane.  A step whose 32 pixels lie inside one row
+                    // below the second one takes left and up without a per-pixel test; when it starts a row only lane 0 differs
+                    // (first column: up and up-up, misc.rs:15-17).  Everything else (the first two rows, steps across a row end,
+                    // the ragged end of the image) goes pixel by pixel through classify_any
+                    const uint32_t wr = a.w;
+                    uint32_t ys = (start + wp0) / wr, xs = (start + wp0) - ys * wr;
                     const uint8_t *pj = pb + wp0 + lane;
                     uint32_t *ij = &S.info[info_index(wp0 + lane)];          // info_index advances by 40 words per 32 pixels
+                    uint32_t jn = wp0 + 32u;                                 // end of the step, as an offset in the band
 #pragma unroll 2
                     for (int s = 0; s < SE_WSTEPS; s++) {
                         uint32_t wd;
-                        if (ys >= 1 && xs >= 1 && xs + 32u <= a.w && wp0 + 32u * s + 32u <= cnt) wd = make_info(pj[0], pj[-1], pj[-w]);
-                        else wd = classify_any(pb, (int)(wp0 + 32u * s + lane), start + wp0 + 32u * s + lane, w, a.npix, plane);
-                        const bool oor = wd >> 31;
-                        const uint32_t act = __ballot_sync(0xffffffffu, oor);
-                        if (act) {
-                            if (oor) {
-                                const uint32_t delta = (wd >> 12) & 255u;
-                                const uint32_t grp = __match_any_sync(act, delta);
-                                const int leader = __ffs(grp) - 1;
-                                uint32_t prev = 0;
-                                if ((int)lane == leader) { prev = cntw[delta]; cntw[delta] = prev + __popc(grp); }
-                                prev = __shfl_sync(act, prev, leader);
-                                wd |= prev + __popc(grp & lt);
-                            }
-                            __syncwarp();
+                        if (ys >= 2 && xs + 32u <= wr && jn <= cnt) {
+                            int v1 = pj[-1], v2 = pj[-w];
+                            if (xs == 0 && lane == 0) { v1 = v2; v2 = jn - 32u >= wr ? (int)pj[-2 * w] : (int)plane[start + jn - 32u - 2u * wr]; }
+                            wd = make_info(pj[0], v1, v2);
+                        } else {
+                            wd = classify_any(pb, (int)(jn - 32u + lane), start + jn - 32u + lane, w, a.npix, plane);
                         }
-                        *ij = wd;
-                        ij += 40; pj += 32;
+                        // stable rank among the warp's pixels of the same context: pixels that are not coded out of range get a
+                        // key of their own (a group of one: rank 0, nothing counted)
+                        const bool oor = wd >> 31;
+                        const uint32_t delta = (wd >> 12) & 255u;
+                        const uint32_t grp = __match_any_sync(0xffffffffu, oor ? delta : 256u + lane);
+                        const int leader = __ffs(grp) - 1;
+                        uint32_t prev = 0;
+                        if (oor && (int)lane == leader) { prev = cntw[delta]; cntw[delta] = prev + __popc(grp); }
+                        prev = __shfl_sync(0xffffffffu, prev, leader);
+                        *ij = wd | (prev + __popc(grp & lt));
+                        __syncwarp();
+                        ij += 40; pj += 32; jn += 32;
                         xs += 32;
-                        while (xs >= a.w) { xs -= a.w; ys++; }
+                        if (xs >= wr) { do { xs -= wr; ys++; } while (xs >= wr); }
                     }
                 }
                 // bases of the warp's segments: exclusive prefix of the counts, every segment padded to a multiple of four
@@ -529,11 +611,11 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                     }
                 }
             }
-            // zero the bit window while the walkers finish (its last reader was the previous band's flush)
-            for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) S.out[i] = 0u;
             SE_CLK(3);
             __syncthreads();
             SE_CLK(4);
+            // the walk is over: its segment tables become the bit window (zeroed here, filled after the next barrier)
+            for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) out[i] = 0u;
 
             // ---- code: 16 consecutive pixels per thread, records stay in registers -------------------------------
             uint32_t r[SE_PPT];
@@ -558,7 +640,7 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 if (lane >= (uint32_t)o) inc += t;
             }
             if (lane == 31) S.wsum[wid] = inc;
-            if (tid == 0) S.out[0] = carry;
+            if (tid == 0) out[0] = carry;
             __syncthreads();
             SE_CLK(5);
             uint32_t pos = carrybits + inc - mylen, band_bits = 0;
@@ -580,9 +662,9 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                     const uint32_t len = rec_len(r[q]);
                     if (len > (uint32_t)REC_SHORT_MAX) {
                         // long unary run: my partial word first, then field by field
-                        if (wv) atomicOr(&S.out[wi], wv);
+                        if (wv) atomicOr(&out[wi], wv);
                         const uint32_t at = (wi << 5) + sh;
-                        pack_long(S.out, r[q], at);
+                        pack_long(out, r[q], at);
                         const uint32_t np2 = at + len;
                         wi = np2 >> 5; sh = np2 & 31u; wv = 0;
                         continue;
@@ -591,48 +673,28 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                     wv |= left >> sh;
                     const uint32_t nsh = sh + len;
                     if (nsh >= 32u) {                                                  // the word is full: sh >= 10 here
-                        atomicOr(&S.out[wi], wv);
+                        atomicOr(&out[wi], wv);
                         wi++;
                         wv = left << (32u - sh);
                     }
                     sh = nsh & 31u;
                 }
-                if (wv) atomicOr(&S.out[wi], wv);
+                if (wv) atomicOr(&out[wi], wv);
                 __syncthreads();
                 const uint32_t nfull = win_bits >> 5;
                 for (uint32_t j = tid; j < nfull; j += SE_THREADS) {
-                    if (wpos + j < slot_words) slot[wpos + j] = bswap32(S.out[j]);
+                    if (wpos + j < slot_words) slot[wpos + j] = bswap32(out[j]);
                 }
                 if (wpos + nfull >= slot_words) ovf = 1;
-                carry = S.out[nfull];
+                carry = out[nfull];
                 wpos += nfull;
             } else {
-                // more than 16 bits per pixel: the band leaves through several windows, every code clipped to the window
-                const uint32_t wbits = (uint32_t)SE_OUT_WORDS * 32u;
-                for (uint32_t w0 = 0; w0 < win_bits; w0 += wbits) {
-                    const uint32_t w1 = w0 + wbits;
-                    if (w0) {
-                        __syncthreads();
-                        for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) S.out[i] = 0u;
-                        __syncthreads();
-                    }
-                    uint32_t off = pos;
+                // more than 16 bits per pixel (rare): the records go to shared memory (the info words are dead) and the band leaves
+                // through several windows, out of line
+                uint32_t *recs = &S.info[tid * SE_PPT];
 #pragma unroll
-                    for (int q = 0; q < SE_PPT; q++) {
-                        const uint32_t len = rec_len(r[q]);
-                        if (len && off < w1 && off + len > w0)
-                            emit_fields(r[q], off, [&](uint32_t o2, uint32_t val, uint32_t nb) { put_clipped(S.out, o2, val, nb, w0, w1); });
-                        off += len;
-                    }
-                    __syncthreads();
-                    const uint32_t nfull = w1 <= win_bits ? (uint32_t)SE_OUT_WORDS : (win_bits - w0) >> 5;
-                    for (uint32_t j = tid; j < nfull; j += SE_THREADS) {
-                        if (wpos + j < slot_words) slot[wpos + j] = bswap32(S.out[j]);
-                    }
-                    if (wpos + nfull >= slot_words) ovf = 1;
-                    carry = w1 <= win_bits ? 0u : S.out[nfull];
-                    wpos += nfull;
-                }
+                for (int q = 0; q < SE_PPT; q++) recs[q] = r[q];
+                pack_windows(out, recs, pos, win_bits, slot, slot_words, wpos, carry, ovf);
             }
             carrybits = win_bits & 31u;
             total_bits += band_bits;

@@ -28,3 +28,14 @@ def tile_batch(n: int, first: int = 0, seed: int = 1) -> np.ndarray:
     for i in range(16):
         pop += (bits >> i) & 1
     return np.clip(base + pop - 8, 0, 255).astype(np.uint8)
+
+
+def mirror_tile(img: np.ndarray, height: int, width: int) -> np.ndarray:
+    """configs[4] "synthetic-resized" (SURVEY.md 8(d) item 5): the image repeated by reflection (period 2H x 2W, so no
+    seams) and cut to height x width.  Works for HxW and HxWx3."""
+    h, w = img.shape[:2]
+    yy = np.arange(height) % (2 * h)
+    xx = np.arange(width) % (2 * w)
+    yy = np.where(yy < h, yy, 2 * h - 1 - yy)
+    xx = np.where(xx < w, xx, 2 * w - 1 - xx)
+    return np.ascontiguousarray(img[yy][:, xx])
