@@ -503,7 +503,7 @@ def run_tiles(args, rig):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "decode": ({"value": all_pixels / (dec_ms * 1e-3) / 1e6, "unit": "MPixel/s", "ms": dec_ms, "lossless": dec_bad == 0.0,
-                        "files": total, "note": "whole shard as one batch, one warp per file"} if decode else None),
+                        "files": total, "note": "whole shard as one batch (k_decode_g8: up to 32 files per warp, one per lane)"} if decode else None),
             "stages_ms_per_step": {k: v[0] / args.steps for k, v in enc_stages.items()},
             "parity": (None if not args.verify else (f"bit-exact vs oracle on {int(n_checked)} sampled tiles" if bad == 0 else f"MISMATCH vs oracle ({int(bad)} of {int(n_checked)})")),
             "stream_redone": codec.stream_redone(),

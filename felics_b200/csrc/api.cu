@@ -134,6 +134,12 @@ int felics_ctx_create(int device, felics_ctx **out) {
         ctx->no_overlap = no && no[0] == '1';
         const char *nh = getenv("FELICS_B200_NO_HOP");       // debug switch: no segment hops
         ctx->no_hop = nh && nh[0] == '1';
+        const char *ng8 = getenv("FELICS_B200_NO_G8");       // debug switch: gray batches decode one file per warp
+        if (ng8 && ng8[0] == '1') ctx->no_g8 = true;
+        const char *g8f = getenv("FELICS_B200_G8_FILES");    // experiment switch: files per warp of the gray batch decoder (1, 2, 4, 8)
+        if (g8f) { const int f = atoi(g8f); if (f == 1 || f == 2 || f == 4 || f == 8 || f == 16 || f == 32) ctx->g8_files_per_warp = f; }
+        const char *g8h = getenv("FELICS_B200_G8_HOT");      // experiment switch: 32 or 64 contexts in shared memory
+        if (g8h && (atoi(g8h) == 8 || atoi(g8h) == 16)) ctx->g8_hot = atoi(g8h);
         const char *nst = getenv("FELICS_B200_NO_STREAM");   // debug/bench switch: gray batches through the multi-kernel pipeline
         ctx->no_stream = nst && nst[0] == '1';
         const char *sdbg = getenv("FELICS_B200_STREAM_DBG");
@@ -159,6 +165,7 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->staging_out) cudaFree(ctx->staging_out);
     if (ctx->tables16) cudaFree(ctx->tables16);
     if (ctx->exact_buf) cudaFree(ctx->exact_buf);
+    if (ctx->g8_cold) cudaFree(ctx->g8_cold);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);

@@ -94,6 +94,11 @@ struct felics_ctx {
     unsigned walk_per_sm = 1;     // walker blocks per SM while the speculative kernels run beside them
     bool no_quads = false;        // debug switch: one sample per thread in the histogram / code kernels
     bool serial16 = false;        // debug switch: the one-warp-per-image 16-bit encoder instead of the parallel one
+    bool no_g8 = false;           // debug switch: gray batches through the one-file-per-warp decoder (k_decode) instead of k_decode_g8
+    int g8_hot = 16;              // experiment switch: contexts whose estimator rows k_decode_g8 keeps in shared memory (32 or 64)
+    void *g8_cold = nullptr;      // k_decode_g8: ticket + estimator rows of the other contexts
+    size_t g8_cold_cap = 0;
+    int g8_files_per_warp = 0;    // experiment switch: files per warp of k_decode_g8 (0 = chosen from the batch size)
     bool no_stream = false;       // debug/bench switch: batches of gray images through the multi-kernel pipeline instead of stream.cu
     size_t stream_min = 96;       // smallest batch the streaming band encoder takes (one block per image: fewer leave SMs idle)
     bool stream_attr_done = false;

@@ -503,6 +503,238 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
     if (lane == 0) a.status[img] = st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batches of 8-bit gray files (BASELINE.json configs[3]): F files per warp, one per lane.  A .fel file is one serial bit
+// chain (compression.rs:151-248), so the batch is the only parallelism -- but a warp that decodes one file on one lane
+// issues every instruction for a single pixel.  Here lanes 0..F-1 of a warp run the same loop on F different files of the
+// same shape: they stay together row by row and pixel by pixel (only the class of the pixel splits them), so an issued
+// instruction serves up to F pixels.  Everything a lane touches per pixel is on chip, interleaved by lane so that lanes at
+// the same position hit different banks: the estimator rows as u16 pairs plus the k that the NEXT out-of-range pixel of the
+// context will use (get_k is computed at update time, off the critical path: one 16-byte load gives the decoder its k), the
+// previous and the current row as bytes.  The pixels leave as bytes, row by row, written by the whole warp: no i16 planes
+// and no unplane pass.  A sample outside 0..255 (no valid file; the reference goes on in i32, compression.rs:305-310), a raw
+// sample outside 0..255 or a residual above 255 hand the file to k_decode_exact (FELICS_NEED_EXACT), which also keeps the
+// u16 counters exact: with residuals <= 255 a counter stays below 2 * (256 / 13) * 1030 < 2^16.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t G8_MAX_W = 4096;
+constexpr int G8_WARPS = 2;
+constexpr int G8_CTX = 256;            // contexts of 8-bit gray samples
+
+struct G8Args {
+    const uint32_t *words;
+    uint64_t arena_words;
+    const uint64_t *offsets;
+    uint8_t *pixels;           // file i at pixels + i * npix
+    int *status;
+    uint4 *cold;               // estimator rows of the contexts >= HOT: [slot][G8_CTX - HOT], tagged with the file (zeroed before the launch)
+    uint32_t *ticket;          // next group of F files (zeroed before the launch)
+    uint32_t w, h, npix;       // w a multiple of 4, 4 <= w <= G8_MAX_W
+    uint32_t word_out;         // pixels is 4-byte aligned: rows leave as words
+};
+
+// read_header order (format.rs:63-84), then decompress_with_header's checks (compression.rs:289-294)
+__device__ __forceinline__ int check_file_header(const uint8_t *hb, uint64_t len, uint8_t color, uint8_t depth, uint32_t w, uint32_t h) {
+    if (len < 4) return FELICS_ERR_IO;
+    if (hb[0] != 'F' || hb[1] != 'L' || hb[2] != 'C' || hb[3] != 'S') return FELICS_ERR_INVALID_SIGNATURE;
+    if (len < 5) return FELICS_ERR_IO;
+    if (hb[4] > 1) return FELICS_ERR_INVALID_COLOR_TYPE;
+    if (len < 6) return FELICS_ERR_IO;
+    if (hb[5] > 1) return FELICS_ERR_INVALID_PIXEL_DEPTH;
+    if (len < FELICS_HEADER_BYTES) return FELICS_ERR_IO;
+    if (hb[4] != color) return FELICS_ERR_INVALID_COLOR_TYPE;
+    if (hb[5] != depth) return FELICS_ERR_INVALID_PIXEL_DEPTH;
+    const uint32_t fw = ((uint32_t)hb[6] << 24) | ((uint32_t)hb[7] << 16) | ((uint32_t)hb[8] << 8) | hb[9];
+    const uint32_t fh = ((uint32_t)hb[10] << 24) | ((uint32_t)hb[11] << 16) | ((uint32_t)hb[12] << 8) | hb[13];
+    if (fw != w || fh != h) return FELICS_ERR_INVALID_DIMENSIONS;
+    return FELICS_OK;
+}
+
+// shared memory of one warp: the hot estimator rows and one pixel row of each of its F files
+__host__ __device__ inline size_t g8_warp_bytes(int F, int hot, uint32_t w) { return (size_t)F * hot * 16 + (((size_t)F * (w / 4) * 4 + 15) & ~(size_t)15); }
+
+// F files per warp, one per lane; the estimator rows of the contexts below HOT live in shared memory, the others (rare in
+// smooth images, and a file's lanes only meet them one pixel at a time) in a tagged table in global memory.  Warps take
+// groups of F files from a ticket until the batch is done.
+template <int F, int HOT>
+__global__ void __launch_bounds__(32 * G8_WARPS) k_decode_g8(G8Args a, uint32_t n) {
+    extern __shared__ __align__(16) unsigned char g8_smem[];
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const uint32_t wq = a.w >> 2;                                          // words per row
+    unsigned char *wbase = g8_smem + (size_t)wid * g8_warp_bytes(F, HOT, a.w);
+    uint4 *tab = reinterpret_cast<uint4 *>(wbase);                          // [HOT][F]: c0|c1<<16, c2|c3<<16, c4|c5<<16, next k
+    uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + (size_t)F * HOT * 16);   // [wq][F]: four samples per word; one row, overwritten in place
+                                                                                   // (sample x of the row above is last needed when sample x is decoded)
+    uint4 *mytab = tab + lane;
+    uint4 *mycold = a.cold + ((size_t)(blockIdx.x * G8_WARPS + wid) * F + (lane < F ? lane : 0)) * (G8_CTX - HOT);
+
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(a.ticket, 1u) * F;
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= n) break;
+        const uint32_t img = first + lane;
+        const bool mine = lane < F && img < n;
+        const uint32_t tag = (img + 1u) << 8;                               // marks the cold rows this file has written
+        for (uint32_t j = lane; j < (uint32_t)HOT * F; j += 32) tab[j] = make_uint4(0u, 0u, 0u, (uint32_t)(NK - 1));   // fresh estimator: get_k of equal counts is the last k
+        __syncwarp();
+
+        int st = FELICS_OK;
+        BitWindow br;
+        int p1 = 0, p2 = 0;
+        if (mine) {
+            const uint64_t off0 = a.offsets[img], off1 = a.offsets[img + 1];
+            st = check_file_header(reinterpret_cast<const uint8_t *>(a.words) + off0, off1 - off0, 0, 0, a.w, a.h);
+            if (st == FELICS_OK) {
+                br.init(a.words, a.arena_words, 8 * (off0 + FELICS_HEADER_BYTES), 8 * off1);
+                p1 = (int)br.read(32);   // read_signed(32) twice (:161-162)
+                p2 = (int)br.read(32);
+                if (br.eof()) st = FELICS_ERR_IO;
+                else if ((uint32_t)p1 > 255u || (uint32_t)p2 > 255u) st = FELICS_NEED_EXACT;
+            }
+        }
+
+        // one pixel (compression.rs:193-246) from its two neighbours; leaves st != OK when the file cannot go on here
+        auto dec = [&](int v1, int v2) -> int {
+            const int hi = max(v1, v2), lo = min(v1, v2);
+            const uint32_t ctx = (uint32_t)(hi - lo);                          // <= 255: every sample so far is 0..255
+            const uint32_t top = br.peek32();
+            int value;
+            if (top >> 31) {                                                    // InRange (:208-215)
+                const uint32_t nn = ctx + 1;
+                const int m = 31 - __clz(nn);
+                const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
+                uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;               // marker + m bits (+ 1): at most 10 bits, all inside the window
+                int used = 1 + m;
+                if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
+                br.skip(used);
+                br.refill();
+                xx += left_p;                                                   // rotate_left (:55-57); xx < nn before
+                if (xx >= nn) xx -= nn;
+                value = lo + (int)xx;
+            } else {
+                const uint32_t above = (top >> 30) & 1u;
+                uint4 *rowp = ctx < (uint32_t)HOT ? mytab + ctx * F : mycold + (ctx - HOT);
+                uint4 r = *rowp;
+                if (ctx >= (uint32_t)HOT) {
+                    if ((r.w & 0xffffff00u) != tag) r = make_uint4(0u, 0u, 0u, (uint32_t)(NK - 1));   // not yet touched by this file
+                    r.w &= 255u;
+                }
+                const uint32_t k = r.w;                                         // get_k (:202), computed when the row was last updated
+                br.skip(2);
+                br.refill();
+                uint32_t q = 0;                                                 // read_unary0
+                for (;;) {
+                    const uint32_t ones = __clz(~br.peek32());                  // 32 when all ones
+                    if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
+                    q += 32; br.skip(32); br.refill();
+                    if (br.eof() || q > 255u) break;
+                }
+                const uint32_t rem = br.read((int)k);
+                if (br.eof()) { st = FELICS_ERR_IO; return 0; }
+                const uint32_t e = (q << k) + rem;
+                if (q > 255u || e > 255u) { st = FELICS_NEED_EXACT; return 0; }
+                // update (parameter_selection.rs:49-65) on u16 pairs: cost of e under k = (e >> k) + 1 + k
+                r.x += (e + 1u) | (((e >> 1) + 2u) << 16);
+                r.y += ((e >> 2) + 3u) | (((e >> 3) + 4u) << 16);
+                r.z += ((e >> 4) + 5u) | (((e >> 5) + 6u) << 16);
+                const uint32_t m2 = __vminu2(__vminu2(r.x, r.y), r.z);
+                if (min(m2 & 0xffffu, m2 >> 16) > HALVE_AT) {
+                    r.x = (r.x >> 1) & 0x7fff7fffu; r.y = (r.y >> 1) & 0x7fff7fffu; r.z = (r.z >> 1) & 0x7fff7fffu;
+                }
+                const uint32_t cc[NK] = {r.x & 0xffffu, r.x >> 16, r.y & 0xffffu, r.y >> 16, r.z & 0xffffu, r.z >> 16};
+                r.w = (uint32_t)argmin_last(cc) | (ctx >= (uint32_t)HOT ? tag : 0u);
+                *rowp = r;
+                value = above ? hi + (int)e + 1 : lo - (int)e - 1;              // (:216-243)
+            }
+            if ((uint32_t)value > 255u) st = FELICS_NEED_EXACT;
+            return value;
+        };
+
+        int col0_b = 0;   // first sample of row y - 2
+        for (uint32_t y = 0; y < a.h; y++) {
+            uint32_t *cur = rows + lane;                                        // word g of my row at cur[g * F]
+            const uint32_t *up = cur;                                           // ... which holds the row above until it is overwritten
+            if (mine && st == FELICS_OK) {
+                if (y == 0) {
+                    // first row: the neighbours are the two samples to the left (misc.rs:8-9)
+                    int l2 = p1, l1 = p2;
+                    uint32_t wv = (uint32_t)p1 | ((uint32_t)p2 << 8);
+                    for (uint32_t x = 2; x < a.w && st == FELICS_OK; x++) {
+                        const int v = dec(l1, l2);
+                        l2 = l1; l1 = v;
+                        if ((x & 3u) == 0) wv = 0;
+                        wv |= (uint32_t)(v & 255) << (8 * (x & 3u));
+                        if ((x & 3u) == 3u) cur[(x >> 2) * F] = wv;
+                    }
+                } else {
+                    // first column: up and up-right on the second row, up and up-up below it (misc.rs:13-17); then left and up
+                    const uint32_t u0 = up[0];
+                    int left = dec((int)(u0 & 255u), y == 1 ? (int)((u0 >> 8) & 255u) : col0_b);
+                    uint32_t wv = (uint32_t)(left & 255);
+                    col0_b = (int)(u0 & 255u);
+#pragma unroll
+                    for (int j = 1; j < 4; j++) {
+                        if (st == FELICS_OK) {
+                            left = dec(left, (int)((u0 >> (8 * j)) & 255u));
+                            wv |= (uint32_t)(left & 255) << (8 * j);
+                        }
+                    }
+                    cur[0] = wv;
+                    for (uint32_t g = 1; g < wq && st == FELICS_OK; g++) {
+                        const uint32_t uw = up[g * F];
+                        left = dec(left, (int)(uw & 255u));
+                        wv = (uint32_t)(left & 255);
+#pragma unroll
+                        for (int j = 1; j < 4; j++) {
+                            if (st == FELICS_OK) {
+                                left = dec(left, (int)((uw >> (8 * j)) & 255u));
+                                wv |= (uint32_t)(left & 255) << (8 * j);
+                            }
+                        }
+                        cur[g * F] = wv;
+                    }
+                }
+                if (st == FELICS_OK && br.eof()) st = FELICS_ERR_IO;   // the reference fails at the read that runs out of input, before any later check
+            }
+            __syncwarp();
+            // the F finished rows leave, every one written by the whole warp (rows of a file that has failed are never read: the
+            // status says so, and a file handed to the exact decoder is written again)
+#pragma unroll 1
+            for (int f = 0; f < F; f++) {
+                if (first + f >= n) break;
+                uint8_t *dst = a.pixels + (size_t)(first + f) * a.npix + (size_t)y * a.w;
+                const uint32_t *src = rows + f;
+                if (a.word_out) {
+                    for (uint32_t g = lane; g < wq; g += 32) reinterpret_cast<uint32_t *>(dst)[g] = src[g * F];
+                } else {
+                    for (uint32_t x = lane; x < a.w; x += 32) dst[x] = (uint8_t)(src[(x >> 2) * F] >> (8 * (x & 3u)));
+                }
+            }
+            __syncwarp();
+        }
+        if (mine) a.status[img] = st;
+    }
+}
+
+template <int F, int HOT>
+int launch_decode_g8(felics_ctx *ctx, G8Args g, size_t n, cudaStream_t st) {
+    const size_t smem = G8_WARPS * g8_warp_bytes(F, HOT, g.w);
+    FELICS_CUDA_TRY(cudaFuncSetAttribute(k_decode_g8<F, HOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1, sms = 148;
+    FELICS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_g8<F, HOT>, 32 * G8_WARPS, smem));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const size_t groups = (n + F - 1) / F;
+    const unsigned blocks = (unsigned)std::min<size_t>((groups + G8_WARPS - 1) / G8_WARPS, (size_t)std::max(per_sm, 1) * sms);
+    const size_t cold_bytes = (size_t)blocks * G8_WARPS * F * (G8_CTX - HOT) * sizeof(uint4);
+    int rc = ensure_buffer(ctx, &ctx->g8_cold, &ctx->g8_cold_cap, cold_bytes + 256);
+    if (rc) return rc;
+    g.ticket = (uint32_t *)ctx->g8_cold;
+    g.cold = (uint4 *)((uint8_t *)ctx->g8_cold + 256);
+    FELICS_CUDA_TRY(cudaMemsetAsync(ctx->g8_cold, 0, cold_bytes + 256, st));
+    k_decode_g8<F, HOT><<<blocks, 32 * G8_WARPS, smem, st>>>(g, (uint32_t)n);
+    return FELICS_OK;
+}
+
 // planes -> pixels with the try_into range checks (compression.rs:305-310, :402-407)
 // distance between consecutive planes, in samples.  One warp per file writes its rows in lockstep with the others:
 // a power-of-two distance would put every file's stores on the same memory channel.
@@ -937,8 +1169,10 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
 
     size_t off_bytes = align_up((n + 1) * sizeof(uint64_t), 256);
     size_t stat_bytes = align_up(n * sizeof(int), 256);
+    // batches of gray files whose rows are whole words: several files per warp, pixels written directly (k_decode_g8)
+    const bool g8 = nch == 1 && hdr.width >= 4 && hdr.width % 4 == 0 && hdr.width <= G8_MAX_W && hdr.height >= 1 && !ctx->no_g8;
     const size_t pstride = plane_stride8(npix);
-    size_t plane_bytes = align_up(((size_t)n * nch * pstride + 8) * sizeof(int16_t), 256);
+    size_t plane_bytes = g8 ? 0 : align_up(((size_t)n * nch * pstride + 8) * sizeof(int16_t), 256);
     int rc = ensure_buffer(ctx, &ctx->scratch, &ctx->scratch_cap, off_bytes + stat_bytes + plane_bytes);
     if (rc) return rc;
     uint8_t *sb = (uint8_t *)ctx->scratch;
@@ -953,7 +1187,28 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
     a.offsets = d_off; a.planes = d_planes; a.status = d_status;
     a.w = hdr.width; a.h = hdr.height; a.npix = npix; a.nch = nch; a.pstride = pstride;
     a.color = hdr.color_type; a.depth = hdr.pixel_depth;
-    {
+    if (g8) {
+        StageScope s(ctx, ST_DECODE);
+        G8Args g;
+        g.words = a.words; g.arena_words = a.arena_words; g.offsets = d_off; g.pixels = (uint8_t *)d_pixels_out; g.status = d_status;
+        g.w = hdr.width; g.h = hdr.height; g.npix = npix; g.word_out = ((uintptr_t)d_pixels_out & 3) == 0 ? 1u : 0u;
+        // files per warp: as many as still leave every SM half a dozen warps of work
+        int F = 1;
+        while (F < 32 && n / (size_t)(2 * F) >= (size_t)148 * 6) F *= 2;
+        if (ctx->g8_files_per_warp) F = ctx->g8_files_per_warp;
+#define G8_LAUNCH(FF) (ctx->g8_hot == 8 ? launch_decode_g8<FF, 8>(ctx, g, n, st) : (ctx->g8_hot == 16 ? launch_decode_g8<FF, 16>(ctx, g, n, st) : launch_decode_g8<FF, 32>(ctx, g, n, st)))
+        switch (F) {
+            case 1: rc = G8_LAUNCH(1); break;
+            case 2: rc = G8_LAUNCH(2); break;
+            case 4: rc = G8_LAUNCH(4); break;
+            case 8: rc = G8_LAUNCH(8); break;
+            case 16: rc = G8_LAUNCH(16); break;
+            default: rc = G8_LAUNCH(32); break;
+        }
+#undef G8_LAUNCH
+        if (rc) return rc;
+        s.launched();
+    } else {
         StageScope s(ctx, ST_DECODE);
         const size_t smem = (size_t)(NBIN - 1) * NK * 4 + 8 + 2 * (size_t)hdr.width * sizeof(int16_t);
         if (hdr.width <= DEC_MAX_W && npix >= 1) {
@@ -967,7 +1222,7 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
         }
         s.launched();
     }
-    if (npix > 0) {
+    if (npix > 0 && !g8) {
         StageScope s(ctx, ST_UNPLANE);
         size_t total = n * (size_t)npix;
         unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 32);

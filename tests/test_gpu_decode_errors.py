@@ -126,3 +126,39 @@ def test_batch_offsets_are_validated(codec):
     assert e.value.code == -12
     out, status = codec.decompress_batch(arena, offsets, hdr)
     assert not status.any() and np.array_equal(out, imgs)
+
+
+@pytest.mark.parametrize("files_per_warp", ["2", "4", "8"])
+def test_damaged_files_inside_a_batch_do_not_disturb_their_neighbours(monkeypatch, files_per_warp):
+    # the gray batch decoder runs several files per warp, one per lane (k_decode_g8): every file must come back with the
+    # oracle's status and pixels whatever happens to the files on the other lanes
+    monkeypatch.setenv("FELICS_B200_G8_FILES", files_per_warp)
+    img = images()["gray8"]
+    rng = np.random.default_rng(99)
+    imgs = [np.clip(img.astype(np.int64) + rng.integers(-3, 4, img.shape), 0, 255).astype(np.uint8) for _ in range(45)]
+    fels = [fo.compress(im) for im in imgs]
+    muts = []
+    for i, fel in enumerate(fels):
+        if i % 3 == 0:
+            muts.append(fel)                                        # every third file stays intact
+        else:
+            muts.append(next(m for k, m in mutations(fel, rng, 7) if k == (i % 6)))
+    offsets = np.zeros(len(muts) + 1, np.uint64)
+    offsets[1:] = np.cumsum([len(m) for m in muts])
+    arena = np.frombuffer(b"".join(muts), dtype=np.uint8)
+    hdr = felics_b200.Header(felics_b200.ColorType.Gray, felics_b200.PixelDepth.Eight, img.shape[1], img.shape[0])
+    with felics_b200.Codec(device=0) as c:
+        out, status = c.decompress_batch(arena, offsets, hdr)
+    seen = set()
+    for i, mut in enumerate(muts):
+        want_rc, want_px = oracle_decode(mut)
+        if want_rc == 0 and want_px.size != img.size:               # a damaged header byte that still parses: another shape, so not this batch's
+            want_rc = None
+        seen.add(want_rc)
+        if want_rc is None:
+            assert status[i] != 0, i
+            continue
+        assert status[i] == want_rc, (i, int(status[i]), want_rc)
+        if want_rc == 0:
+            assert np.array_equal(out[i].reshape(-1), want_px), i
+    assert 0 in seen and len(seen) >= 3, seen
