@@ -166,6 +166,8 @@ void felics_ctx_destroy(felics_ctx *ctx) {
     if (ctx->tables16) cudaFree(ctx->tables16);
     if (ctx->exact_buf) cudaFree(ctx->exact_buf);
     if (ctx->g8_cold) cudaFree(ctx->g8_cold);
+    if (ctx->v_in) cudaFree(ctx->v_in);
+    if (ctx->v_out) cudaFree(ctx->v_out);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
@@ -339,6 +341,9 @@ struct HeaderKey {
 };
 }  // namespace
 
+// Images travel in chunks of consecutive images (about 1 GiB of pixels): every image is copied from the caller's memory
+// straight into a device buffer, next to the other images of its shape; each shape is encoded as one device batch; the
+// streams go from the device straight to their places in the caller's arena.  No host-side staging copy.
 int felics_compress_batch_v(felics_ctx *ctx, size_t n, const void *const *pixels, const felics_header *hdrs, uint8_t *arena, size_t arena_cap,
                             uint64_t *offsets) {
     if (!ctx || !offsets || (n && (!pixels || !hdrs || !arena))) { set_error("null argument"); return FELICS_ERR_INVALID_ARGUMENT; }
@@ -346,45 +351,87 @@ int felics_compress_batch_v(felics_ctx *ctx, size_t n, const void *const *pixels
     if (rc) return rc;
     offsets[0] = 0;
     if (n == 0) return FELICS_OK;
-    std::map<HeaderKey, std::vector<size_t>> groups;
     for (size_t i = 0; i < n; i++) {
         if ((rc = check_header(&hdrs[i]))) return rc;
         if (!pixels[i] && felics_pixel_bytes(&hdrs[i])) { set_error("null pixels for image %zu", i); return FELICS_ERR_INVALID_ARGUMENT; }
-        groups[HeaderKey{hdrs[i].color_type, hdrs[i].pixel_depth, hdrs[i].width, hdrs[i].height}].push_back(i);
     }
-    // every group is encoded as one batch of equally shaped images into a host buffer of its own; the streams are put in
-    // image order once all sizes are known
-    std::vector<uint64_t> sizes(n, 0);
-    std::vector<std::pair<const std::vector<size_t> *, std::vector<uint8_t>>> done;
-    std::vector<std::vector<uint64_t>> goffs;
-    done.reserve(groups.size());
-    for (auto &kv : groups) {
-        const std::vector<size_t> &idx = kv.second;
-        const felics_header hdr = hdrs[idx[0]];
-        const size_t per = felics_pixel_bytes(&hdr), m = idx.size();
-        std::vector<uint8_t> in(per * m + 16);
-        for (size_t j = 0; j < m; j++)
-            if (per) memcpy(in.data() + j * per, pixels[idx[j]], per);
-        std::vector<uint64_t> off(m + 1, 0);
-        std::vector<uint8_t> out(per * m / 2 + 64 * m + 4096);
-        rc = felics_compress_batch(ctx, m, in.data(), &hdr, out.data(), out.size(), off.data());
-        if (rc == FELICS_ERR_BUFFER_TOO_SMALL) {
-            out.resize((size_t)off[m] + 64);
-            rc = felics_compress_batch(ctx, m, in.data(), &hdr, out.data(), out.size(), off.data());
+    cudaStream_t st = ctx->stream;
+    const size_t chunk_bytes = (size_t)1 << 30;
+    bool too_small = false;
+    struct Group { felics_header hdr; std::vector<size_t> idx; size_t in_base, out_base, out_cap; std::vector<uint64_t> off; std::vector<uint8_t> bounce; };
+    for (size_t c0 = 0; c0 < n;) {
+        size_t c1 = c0, bytes = 0;
+        while (c1 < n && (c1 == c0 || bytes + felics_pixel_bytes(&hdrs[c1]) <= chunk_bytes)) bytes += felics_pixel_bytes(&hdrs[c1++]);
+        std::map<HeaderKey, size_t> index;
+        std::vector<Group> groups;
+        for (size_t i = c0; i < c1; i++) {
+            const HeaderKey key{hdrs[i].color_type, hdrs[i].pixel_depth, hdrs[i].width, hdrs[i].height};
+            auto it = index.find(key);
+            if (it == index.end()) { it = index.emplace(key, groups.size()).first; groups.push_back(Group{hdrs[i], {}, 0, 0, 0, {}, {}}); }
+            groups[it->second].idx.push_back(i);
         }
-        if (rc) return rc;
-        for (size_t j = 0; j < m; j++) sizes[idx[j]] = off[j + 1] - off[j];
-        done.emplace_back(&idx, std::move(out));
-        goffs.push_back(std::move(off));
+        size_t in_total = 0, out_total = 0;
+        for (Group &g : groups) {
+            const size_t per = felics_pixel_bytes(&g.hdr), m = g.idx.size();
+            g.in_base = in_total; in_total = align_up(in_total + per * m + 16, 256);
+            g.out_cap = per * m + per * m / 4 + 256 * m + 4096;      // uniform noise needs about 9 / 8 of the input
+            g.out_base = out_total; out_total = align_up(out_total + g.out_cap, 256);
+            g.off.assign(m + 1, 0);
+        }
+        if ((rc = ensure_buffer(ctx, &ctx->v_in, &ctx->v_in_cap, in_total + 256))) return rc;
+        if ((rc = ensure_buffer(ctx, &ctx->v_out, &ctx->v_out_cap, out_total + 256))) return rc;
+        for (Group &g : groups) {
+            const size_t per = felics_pixel_bytes(&g.hdr);
+            if (!per) continue;
+            for (size_t j = 0; j < g.idx.size(); j++)
+                FELICS_CUDA_TRY(cudaMemcpyAsync((uint8_t *)ctx->v_in + g.in_base + j * per, pixels[g.idx[j]], per, cudaMemcpyHostToDevice, st));
+        }
+        for (Group &g : groups) {
+            rc = encode_batch_device(ctx, g.idx.size(), (const uint8_t *)ctx->v_in + g.in_base, g.hdr, (uint8_t *)ctx->v_out + g.out_base, nullptr, g.out_cap,
+                                     g.off.data());
+            if (rc == FELICS_ERR_BUFFER_TOO_SMALL) {
+                // the sizes are exact: a buffer of its own for this group (only data that expands by more than a quarter gets here)
+                const size_t need = (size_t)g.off[g.idx.size()] + 256;
+                void *big = nullptr;
+                FELICS_CUDA_TRY(cudaMalloc(&big, need));
+                rc = encode_batch_device(ctx, g.idx.size(), (const uint8_t *)ctx->v_in + g.in_base, g.hdr, (uint8_t *)big, nullptr, need, g.off.data());
+                if (!rc && !too_small) {
+                    // copied out below needs the stream in v_out: it does not fit there, so place this group's images now, at offsets known only
+                    // once the earlier images of the chunk are sized -- fall back to a host bounce for this rare case
+                    std::vector<uint8_t> bounce((size_t)g.off[g.idx.size()]);
+                    if (cudaMemcpyAsync(bounce.data(), big, bounce.size(), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) rc = FELICS_ERR_CUDA;
+                    g.bounce.swap(bounce);
+                }
+                cudaFree(big);
+            }
+            if (rc) return rc;
+        }
+        // sizes of the chunk's images, in image order
+        std::vector<std::pair<uint32_t, uint32_t>> where(c1 - c0);   // image -> (group, position in the group)
+        for (size_t gi = 0; gi < groups.size(); gi++)
+            for (size_t j = 0; j < groups[gi].idx.size(); j++) where[groups[gi].idx[j] - c0] = {(uint32_t)gi, (uint32_t)j};
+        for (size_t i = c0; i < c1; i++) {
+            const Group &g = groups[where[i - c0].first];
+            const size_t j = where[i - c0].second;
+            offsets[i + 1] = offsets[i] + (g.off[j + 1] - g.off[j]);
+        }
+        if (offsets[c1] > arena_cap) too_small = true;
+        if (!too_small) {
+            for (size_t i = c0; i < c1; i++) {
+                const Group &g = groups[where[i - c0].first];
+                const size_t j = where[i - c0].second;
+                const size_t len = (size_t)(g.off[j + 1] - g.off[j]);
+                if (!len) continue;
+                if (!g.bounce.empty()) memcpy(arena + offsets[i], g.bounce.data() + g.off[j], len);
+                else FELICS_CUDA_TRY(cudaMemcpyAsync(arena + offsets[i], (const uint8_t *)ctx->v_out + g.out_base + g.off[j], len, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        FELICS_CUDA_TRY(cudaStreamSynchronize(st));   // the caller's pixels have been read, its arena written; v_in / v_out are free again
+        c0 = c1;
     }
-    for (size_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + sizes[i];
-    if (offsets[n] > arena_cap) {
+    if (too_small) {
         set_error("output capacity %zu too small (need %llu)", arena_cap, (unsigned long long)offsets[n]);
         return FELICS_ERR_BUFFER_TOO_SMALL;
-    }
-    for (size_t g = 0; g < done.size(); g++) {
-        const std::vector<size_t> &idx = *done[g].first;
-        for (size_t j = 0; j < idx.size(); j++) memcpy(arena + offsets[idx[j]], done[g].second.data() + goffs[g][j], (size_t)sizes[idx[j]]);
     }
     return FELICS_OK;
 }
@@ -396,35 +443,61 @@ int felics_decompress_batch_v(felics_ctx *ctx, size_t n, const uint8_t *arena, c
     if (rc) return rc;
     if (n == 0) return FELICS_OK;
     if ((rc = check_offsets(n, offsets))) return rc;
-    std::map<HeaderKey, std::vector<size_t>> groups;
+    cudaStream_t st = ctx->stream;
+    std::vector<felics_header> hs(n);
+    std::vector<uint8_t> ok(n, 0);
     for (size_t i = 0; i < n; i++) {
-        felics_header h;
-        status[i] = felics_read_header(arena + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), &h);   // read_header's own errors (format.rs:63-84)
+        status[i] = felics_read_header(arena + offsets[i], (size_t)(offsets[i + 1] - offsets[i]), &hs[i]);   // read_header's own errors (format.rs:63-84)
         if (status[i]) continue;
-        if (hdrs_out) hdrs_out[i] = h;
-        const uint64_t npix = (uint64_t)h.width * h.height;
+        if (hdrs_out) hdrs_out[i] = hs[i];
+        const uint64_t npix = (uint64_t)hs[i].width * hs[i].height;
         if (npix > 0xffffffffull) { status[i] = FELICS_ERR_INVALID_DIMENSIONS; continue; }   // checked_mul (compression.rs:176-180)
-        if (felics_pixel_bytes(&h) > caps[i]) { status[i] = FELICS_ERR_BUFFER_TOO_SMALL; continue; }
-        groups[HeaderKey{h.color_type, h.pixel_depth, h.width, h.height}].push_back(i);
+        if (felics_pixel_bytes(&hs[i]) > caps[i]) { status[i] = FELICS_ERR_BUFFER_TOO_SMALL; continue; }
+        ok[i] = 1;
     }
-    for (auto &kv : groups) {
-        const std::vector<size_t> &idx = kv.second;
-        felics_header hdr;
-        hdr.color_type = kv.first.color; hdr.pixel_depth = kv.first.depth; hdr.width = kv.first.w; hdr.height = kv.first.h;
-        const size_t per = felics_pixel_bytes(&hdr), m = idx.size();
-        std::vector<uint64_t> off(m + 1, 0);
-        for (size_t j = 0; j < m; j++) off[j + 1] = off[j] + (offsets[idx[j] + 1] - offsets[idx[j]]);
-        std::vector<uint8_t> in((size_t)off[m] + 16), out(per * m + 16);
-        for (size_t j = 0; j < m; j++) memcpy(in.data() + off[j], arena + offsets[idx[j]], (size_t)(off[j + 1] - off[j]));
-        std::vector<int> st(m, 0);
-        rc = felics_decompress_batch(ctx, m, in.data(), off.data(), &hdr, out.data(), st.data());
-        bool per_image = false;
-        for (size_t j = 0; j < m; j++) per_image |= st[j] == rc;
-        if (rc && !per_image) return rc;   // a failure of the call, not of one file
-        for (size_t j = 0; j < m; j++) {
-            status[idx[j]] = st[j];
-            if (st[j] == FELICS_OK && per) memcpy(pixels_out[idx[j]], out.data() + j * per, per);
+    const size_t chunk_bytes = (size_t)1 << 30;
+    struct Group { felics_header hdr; std::vector<size_t> idx; std::vector<uint64_t> off; size_t in_base, out_base; };
+    for (size_t c0 = 0; c0 < n;) {
+        size_t c1 = c0, bytes = 0;
+        while (c1 < n && (c1 == c0 || bytes + (ok[c1] ? felics_pixel_bytes(&hs[c1]) : 0) <= chunk_bytes)) { bytes += ok[c1] ? felics_pixel_bytes(&hs[c1]) : 0; c1++; }
+        std::map<HeaderKey, size_t> index;
+        std::vector<Group> groups;
+        for (size_t i = c0; i < c1; i++) {
+            if (!ok[i]) continue;
+            const HeaderKey key{hs[i].color_type, hs[i].pixel_depth, hs[i].width, hs[i].height};
+            auto it = index.find(key);
+            if (it == index.end()) { it = index.emplace(key, groups.size()).first; groups.push_back(Group{hs[i], {}, {}, 0, 0}); }
+            groups[it->second].idx.push_back(i);
         }
+        size_t in_total = 0, out_total = 0;
+        for (Group &g : groups) {
+            const size_t m = g.idx.size();
+            g.off.assign(m + 1, 0);
+            for (size_t j = 0; j < m; j++) g.off[j + 1] = g.off[j] + (offsets[g.idx[j] + 1] - offsets[g.idx[j]]);
+            g.in_base = in_total; in_total = align_up(in_total + (size_t)g.off[m] + 16, 256);
+            g.out_base = out_total; out_total = align_up(out_total + felics_pixel_bytes(&g.hdr) * m + 16, 256);
+        }
+        if ((rc = ensure_buffer(ctx, &ctx->v_in, &ctx->v_in_cap, in_total + 256))) return rc;
+        if ((rc = ensure_buffer(ctx, &ctx->v_out, &ctx->v_out_cap, out_total + 256))) return rc;
+        for (Group &g : groups)
+            for (size_t j = 0; j < g.idx.size(); j++)
+                if (g.off[j + 1] > g.off[j])
+                    FELICS_CUDA_TRY(cudaMemcpyAsync((uint8_t *)ctx->v_in + g.in_base + g.off[j], arena + offsets[g.idx[j]], (size_t)(g.off[j + 1] - g.off[j]), cudaMemcpyHostToDevice, st));
+        for (Group &g : groups) {
+            const size_t per = felics_pixel_bytes(&g.hdr), m = g.idx.size();
+            std::vector<int> sg(m, 0);
+            rc = decode_batch_device(ctx, m, (const uint8_t *)ctx->v_in + g.in_base, g.off.data(), g.hdr, (uint8_t *)ctx->v_out + g.out_base, sg.data());
+            bool per_image = false;
+            for (size_t j = 0; j < m; j++) per_image |= sg[j] == rc;
+            if (rc && !per_image) return rc;   // a failure of the call, not of one file
+            for (size_t j = 0; j < m; j++) {
+                status[g.idx[j]] = sg[j];
+                if (sg[j] == FELICS_OK && per)
+                    FELICS_CUDA_TRY(cudaMemcpyAsync(pixels_out[g.idx[j]], (const uint8_t *)ctx->v_out + g.out_base + j * per, per, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        FELICS_CUDA_TRY(cudaStreamSynchronize(st));
+        c0 = c1;
     }
     for (size_t i = 0; i < n; i++)
         if (status[i]) return status[i];

@@ -60,6 +60,10 @@ struct felics_ctx {
 
     void *scratch = nullptr;      // device scratch, grown on demand
     size_t scratch_cap = 0;
+    void *v_in = nullptr;         // device buffers of the mixed-shape batch calls (felics_*_batch_v)
+    size_t v_in_cap = 0;
+    void *v_out = nullptr;
+    size_t v_out_cap = 0;
     void *staging_in = nullptr;   // device staging for host-memory entry points
     size_t staging_in_cap = 0;
     void *staging_out = nullptr;

@@ -492,24 +492,33 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 __syncwarp();
                 const uint32_t wp0 = wid * SE_WPIX;
                 {
-                    // position of the step's first pixel: the same in every lane.  A step whose 32 pixels lie inside one row
-                    // below the second one takes left and up without a per-pixel test; when it starts a row only lane 0 differs
-                    // (first column: up and up-up, misc.rs:15-17).  Everything else (the first two rows, steps across a row end,
-                    // the ragged end of the image) goes pixel by pixel through classify_any
+                    // A step whose 32 pixels lie inside one row below the second one takes left and up without a per-pixel test; when
+                    // it starts a row only lane 0 differs (first column: up and up-up, misc.rs:15-17).  Everything else (the first two
+                    // rows, steps across a row end, the ragged end of the image) goes pixel by pixel through classify_any.  Which step
+                    // is which is settled once per band: lane s looks at step s, two ballots keep the answers
                     const uint32_t wr = a.w;
-                    uint32_t ys = (start + wp0) / wr, xs = (start + wp0) - ys * wr;
+                    uint32_t slow, rowstart;
+                    {
+                        const uint32_t j0 = wp0 + 32u * lane, i0 = start + j0;
+                        const uint32_t y0 = i0 / wr, x0 = i0 - y0 * wr;
+                        const bool mine = lane < (uint32_t)SE_WSTEPS;
+                        slow = __ballot_sync(0xffffffffu, mine && !(y0 >= 2 && x0 + 32u <= wr && j0 + 32u <= cnt));
+                        rowstart = __ballot_sync(0xffffffffu, mine && x0 == 0) & ~slow;
+                    }
                     const uint8_t *pj = pb + wp0 + lane;
                     uint32_t *ij = &S.info[info_index(wp0 + lane)];          // info_index advances by 40 words per 32 pixels
-                    uint32_t jn = wp0 + 32u;                                 // end of the step, as an offset in the band
 #pragma unroll 2
                     for (int s = 0; s < SE_WSTEPS; s++) {
                         uint32_t wd;
-                        if (ys >= 2 && xs + 32u <= wr && jn <= cnt) {
+                        if (!((slow >> s) & 1u)) {
                             int v1 = pj[-1], v2 = pj[-w];
-                            if (xs == 0 && lane == 0) { v1 = v2; v2 = jn - 32u >= wr ? (int)pj[-2 * w] : (int)plane[start + jn - 32u - 2u * wr]; }
+                            if (((rowstart >> s) & 1u) && lane == 0) {
+                                const uint32_t j = wp0 + 32u * s;
+                                v1 = v2; v2 = j >= wr ? (int)pj[-2 * w] : (int)plane[start + j - 2u * wr];
+                            }
                             wd = make_info(pj[0], v1, v2);
                         } else {
-                            wd = classify_any(pb, (int)(jn - 32u + lane), start + jn - 32u + lane, w, a.npix, plane);
+                            wd = classify_any(pb, (int)(wp0 + 32u * s + lane), start + wp0 + 32u * s + lane, w, a.npix, plane);
                         }
                         // stable rank among the warp's pixels of the same context: pixels that are not coded out of range get a
                         // key of their own (a group of one: rank 0, nothing counted)
@@ -522,9 +531,7 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                         prev = __shfl_sync(0xffffffffu, prev, leader);
                         *ij = wd | (prev + __popc(grp & lt));
                         __syncwarp();
-                        ij += 40; pj += 32; jn += 32;
-                        xs += 32;
-                        if (xs >= wr) { do { xs -= wr; ys++; } while (xs >= wr); }
+                        ij += 40; pj += 32;
                     }
                 }
                 // bases of the warp's segments: exclusive prefix of the counts, every segment padded to a multiple of four
