@@ -136,16 +136,24 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel, workload):
+def recorded_traffic(kernel, workload, units_per_launch=None):
     """dram bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/traffic.json
-    names the capture, its command and the git revision it was taken at); None when there is no capture."""
+    names the capture, its command and the git revision it was taken at); None when there is no capture.  Workloads whose
+    launches vary in size record bytes per unit (tile) and are scaled to the units one launch of this run covers.
+    Returns (bytes, source)."""
     p = ROOT / "profiles" / "traffic.json"
-    if p.exists():
-        try:
-            return json.loads(p.read_text()).get(workload, {}).get(kernel)
-        except Exception:
-            return None
-    return None
+    if not p.exists():
+        return None, None
+    try:
+        w = json.loads(p.read_text()).get(workload, {})
+        cap = w.get("_capture", {})
+        src = f"profiles/traffic.json[{workload}]: {cap.get('files', '?')} at git {cap.get('git', '?')}"
+        per = w.get("_per_unit", {})
+        if units_per_launch is not None and kernel in per:
+            return per[kernel] * units_per_launch, src
+        return w.get(kernel), (src if kernel in w else None)
+    except Exception:
+        return None, None
 
 
 TOTAL_TILES = 65536
@@ -342,7 +350,7 @@ def encode_host_call(rig, n_img, pin_in, chdr, pin_out, cap, host_offsets):
         raise RuntimeError(f"felics_compress_batch failed: {rc} {rig.lib.felics_last_error().decode()}")
 
 
-def roofline_of(stages, steps, alg_bytes_per_step, total_ms, workload):
+def roofline_of(stages, steps, alg_bytes_per_step, total_ms, workload, units_per_step=None):
     peak, peak_src = measured_peak_gbs()
     dom = max(stages, key=lambda k: stages[k][0])
     dom_ms, dom_launches = stages[dom]
@@ -351,8 +359,9 @@ def roofline_of(stages, steps, alg_bytes_per_step, total_ms, workload):
     per_launch = alg_bytes_per_step / launches_per_step
     achieved = per_launch / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
     whole = alg_bytes_per_step * steps / (total_ms * 1e-3) / 1e9
+    traffic, traffic_src = recorded_traffic(dom, workload, None if units_per_step is None else units_per_step / launches_per_step)
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": recorded_traffic(dom, workload), "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_launch,
             "kernel_ms_per_launch": dom_avg_ms, "kernel_launches_per_step": launches_per_step, "whole_encode_achieved_gbs": whole,
             "whole_encode_frac": whole / peak}
 
@@ -473,7 +482,7 @@ def run_tiles(args, rig):
     line = None
     if rig.rank == 0:
         enc_stages = {k: v for k, v in stages.items() if k not in ("decode", "unplane") and v[1]}
-        roof = roofline_of(enc_stages, args.steps, in_bytes + fel_bytes, sum(ms_dev), "tiles")
+        roof = roofline_of(enc_stages, args.steps, in_bytes + fel_bytes, sum(ms_dev), "tiles", units_per_step=count)
         # CPU baseline on this box's host cores: the oracle port on a bounded sample of the same tiles
         info = cpu_info()
         n1 = min(count, 256)

@@ -138,8 +138,6 @@ int felics_ctx_create(int device, felics_ctx **out) {
         if (ng8 && ng8[0] == '1') ctx->no_g8 = true;
         const char *g8f = getenv("FELICS_B200_G8_FILES");    // experiment switch: files per warp of the gray batch decoder (1, 2, 4, 8)
         if (g8f) { const int f = atoi(g8f); if (f == 1 || f == 2 || f == 4 || f == 8 || f == 16 || f == 32) ctx->g8_files_per_warp = f; }
-        const char *g8h = getenv("FELICS_B200_G8_HOT");      // experiment switch: 32 or 64 contexts in shared memory
-        if (g8h && (atoi(g8h) == 8 || atoi(g8h) == 16)) ctx->g8_hot = atoi(g8h);
         const char *nst = getenv("FELICS_B200_NO_STREAM");   // debug/bench switch: gray batches through the multi-kernel pipeline
         ctx->no_stream = nst && nst[0] == '1';
         const char *sdbg = getenv("FELICS_B200_STREAM_DBG");

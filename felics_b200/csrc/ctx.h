@@ -99,7 +99,6 @@ struct felics_ctx {
     bool no_quads = false;        // debug switch: one sample per thread in the histogram / code kernels
     bool serial16 = false;        // debug switch: the one-warp-per-image 16-bit encoder instead of the parallel one
     bool no_g8 = false;           // debug switch: gray batches through the one-file-per-warp decoder (k_decode) instead of k_decode_g8
-    int g8_hot = 16;              // experiment switch: contexts whose estimator rows k_decode_g8 keeps in shared memory (32 or 64)
     void *g8_cold = nullptr;      // k_decode_g8: ticket + estimator rows of the other contexts
     size_t g8_cold_cap = 0;
     int g8_files_per_warp = 0;    // experiment switch: files per warp of k_decode_g8 (0 = chosen from the batch size)

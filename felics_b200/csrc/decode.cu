@@ -519,6 +519,8 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
 constexpr uint32_t G8_MAX_W = 4096;
 constexpr int G8_WARPS = 2;
 constexpr int G8_CTX = 256;            // contexts of 8-bit gray samples
+constexpr int G8_HOT = 16;             // contexts whose estimator rows live in shared memory (measured on the configs[3] tiles, 32 files per warp:
+                                       // 8 -> 39.7, 16 -> 47.6, 32 -> 26.1 GPixel/s: fewer rows = more warps per SM, more rows = fewer trips to global memory)
 
 struct G8Args {
     const uint32_t *words;
@@ -1196,7 +1198,7 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
         int F = 1;
         while (F < 32 && n / (size_t)(2 * F) >= (size_t)148 * 6) F *= 2;
         if (ctx->g8_files_per_warp) F = ctx->g8_files_per_warp;
-#define G8_LAUNCH(FF) (ctx->g8_hot == 8 ? launch_decode_g8<FF, 8>(ctx, g, n, st) : (ctx->g8_hot == 16 ? launch_decode_g8<FF, 16>(ctx, g, n, st) : launch_decode_g8<FF, 32>(ctx, g, n, st)))
+#define G8_LAUNCH(FF) launch_decode_g8<FF, G8_HOT>(ctx, g, n, st)
         switch (F) {
             case 1: rc = G8_LAUNCH(1); break;
             case 2: rc = G8_LAUNCH(2); break;
