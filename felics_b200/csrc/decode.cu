@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(32) k_decode(DecArgs a, uint32_t n) {
 // sample outside 0..255 or a residual above 255 hand the file to k_decode_exact (FELICS_NEED_EXACT), which also keeps the
 // u16 counters exact: with residuals <= 255 a counter stays below 2 * (256 / 13) * 1030 < 2^16.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t G8_MAX_W = 4096;
+constexpr uint32_t G8_MAX_W = 32768;    // one pixel row per file in shared memory
 constexpr int G8_WARPS = 2;
 constexpr int G8_CTX = 256;            // contexts of 8-bit gray samples
 constexpr int G8_HOT = 16;             // contexts whose estimator rows live in shared memory (measured on the configs[3] tiles, 32 files per warp:
@@ -1196,11 +1196,16 @@ int decode_batch_device(felics_ctx *ctx, size_t n, const uint8_t *d_arena, const
         g.w = hdr.width; g.h = hdr.height; g.npix = npix; g.word_out = ((uintptr_t)d_pixels_out & 3) == 0 ? 1u : 0u;
         // files per warp: as many as still leave every SM half a dozen warps of work
         int F = 1;
-        while (F < 32 && n / (size_t)(2 * F) >= (size_t)148 * 6) F *= 2;
-        if (ctx->g8_files_per_warp) F = ctx->g8_files_per_warp;
+        const size_t warp_budget = 100 * 1024;   // shared memory of one warp (two warps per block)
+        while (F < 32 && n / (size_t)(2 * F) >= (size_t)148 * 6 && g8_warp_bytes(2 * F, G8_HOT, hdr.width) <= warp_budget) F *= 2;
+        if (g8_warp_bytes(1, G8_CTX, hdr.width) > warp_budget) F = std::max(F, 2);   // (rows of 32,768 samples: the hot / cold split even for one file)
+        if (ctx->g8_files_per_warp) {
+            F = ctx->g8_files_per_warp;
+            while (F > 1 && g8_warp_bytes(F, G8_HOT, hdr.width) > warp_budget) F /= 2;
+        }
 #define G8_LAUNCH(FF) launch_decode_g8<FF, G8_HOT>(ctx, g, n, st)
         switch (F) {
-            case 1: rc = G8_LAUNCH(1); break;
+            case 1: rc = launch_decode_g8<1, G8_CTX>(ctx, g, n, st); break;   // a warp per file: room for every estimator row
             case 2: rc = G8_LAUNCH(2); break;
             case 4: rc = G8_LAUNCH(4); break;
             case 8: rc = G8_LAUNCH(8); break;

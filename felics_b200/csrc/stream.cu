@@ -960,7 +960,10 @@ int stream_encode_batch_host(felics_ctx *ctx, size_t n, const void *h_pixels, co
     StreamPlan pl;
     int rc = stream_plan(ctx, hdr, true, pl);
     if (rc) return rc;
-    size_t sub = std::max<size_t>(32, (n + 7) / 8);                                       // at least eight sub-batches to overlap
+    // eight to thirty-two sub-batches to overlap (what does not overlap is the first copy in, the last encode and the last
+    // copy out), none smaller than two waves of blocks
+    const size_t nsub_want = std::min<size_t>(32, std::max<size_t>(8, n / ((size_t)2 * 148 * SE_CTAS_PER_SM)));
+    size_t sub = std::max<size_t>(32, (n + nsub_want - 1) / nsub_want);
     sub = std::min(sub, std::max<size_t>(1, ((size_t)1 << 30) / pl.slot_bytes));           // at most 1 GB of slots
     sub = std::min(sub, n);
     const size_t nsub = (n + sub - 1) / sub;
