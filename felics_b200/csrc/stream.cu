@@ -491,47 +491,66 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 for (int q = 0; q < SE_WREG / 128; q++) reinterpret_cast<uint32_t *>(ecw)[q * 32 + lane] = 0xffffffffu;   // null elements
                 __syncwarp();
                 const uint32_t wp0 = wid * SE_WPIX;
+                // classify: every thread takes 16 consecutive pixels (the 512 of a warp's 32 threads are the warp's own).  A run
+                // inside one row below the second one reads its 16 samples and the 16 above them as eight words and carries the
+                // left neighbour in a register; when it starts a row its first pixel takes up and up-up (misc.rs:15-17).
+                // Everything else (the first two rows, runs across a row end, the ragged end of the image) goes pixel by pixel
+                // through classify_any
                 {
-                    // A step whose 32 pixels lie inside one row below the second one takes left and up without a per-pixel test; when
-                    // it starts a row only lane 0 differs (first column: up and up-up, misc.rs:15-17).  Everything else (the first two
-                    // rows, steps across a row end, the ragged end of the image) goes pixel by pixel through classify_any.  Which step
-                    // is which is settled once per band: lane s looks at step s, two ballots keep the answers
                     const uint32_t wr = a.w;
-                    uint32_t slow, rowstart;
-                    {
-                        const uint32_t j0 = wp0 + 32u * lane, i0 = start + j0;
-                        const uint32_t y0 = i0 / wr, x0 = i0 - y0 * wr;
-                        const bool mine = lane < (uint32_t)SE_WSTEPS;
-                        slow = __ballot_sync(0xffffffffu, mine && !(y0 >= 2 && x0 + 32u <= wr && j0 + 32u <= cnt));
-                        rowstart = __ballot_sync(0xffffffffu, mine && x0 == 0) & ~slow;
-                    }
-                    const uint8_t *pj = pb + wp0 + lane;
-                    uint32_t *ij = &S.info[info_index(wp0 + lane)];          // info_index advances by 40 words per 32 pixels
-#pragma unroll 2
-                    for (int s = 0; s < SE_WSTEPS; s++) {
-                        uint32_t wd;
-                        if (!((slow >> s) & 1u)) {
-                            int v1 = pj[-1], v2 = pj[-w];
-                            if (((rowstart >> s) & 1u) && lane == 0) {
-                                const uint32_t j = wp0 + 32u * s;
-                                v1 = v2; v2 = j >= wr ? (int)pj[-2 * w] : (int)plane[start + j - 2u * wr];
+                    const uint32_t j0 = tid * SE_PPT, i0 = start + j0;
+                    const uint32_t y0 = i0 / wr, x0 = i0 - y0 * wr;
+                    uint4 *iw = reinterpret_cast<uint4 *>(&S.info[info_index(j0)]);
+                    if (y0 >= 2 && x0 + (uint32_t)SE_PPT <= wr && j0 + (uint32_t)SE_PPT <= cnt) {
+                        const uint32_t *cw = reinterpret_cast<const uint32_t *>(pb + j0);       // the band starts on a 16-byte boundary
+                        const uint32_t *uw = reinterpret_cast<const uint32_t *>(pb + j0 - w);   // the width is a multiple of four
+                        int left, upup = 0;
+                        if (x0 == 0) { left = -1; upup = j0 >= wr ? (int)pb[(int)j0 - 2 * w] : (int)plane[i0 - 2u * wr]; }
+                        else left = pb[(int)j0 - 1];
+#pragma unroll
+                        for (int q = 0; q < SE_PPT / 4; q++) {
+                            const uint32_t c = cw[q], u = uw[q];
+                            uint32_t wd[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const int p = (int)((c >> (8 * k)) & 255u), up = (int)((u >> (8 * k)) & 255u);
+                                if (q == 0 && k == 0) wd[k] = left < 0 ? make_info(p, up, upup) : make_info(p, left, up);
+                                else wd[k] = make_info(p, left, up);
+                                left = p;
                             }
-                            wd = make_info(pj[0], v1, v2);
-                        } else {
-                            wd = classify_any(pb, (int)(wp0 + 32u * s + lane), start + wp0 + 32u * s + lane, w, a.npix, plane);
+                            iw[q] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
                         }
-                        // stable rank among the warp's pixels of the same context: pixels that are not coded out of range get a
-                        // key of their own (a group of one: rank 0, nothing counted)
-                        const bool oor = wd >> 31;
-                        const uint32_t delta = (wd >> 12) & 255u;
-                        const uint32_t grp = __match_any_sync(0xffffffffu, oor ? delta : 256u + lane);
-                        const int leader = __ffs(grp) - 1;
-                        uint32_t prev = 0;
-                        if (oor && (int)lane == leader) { prev = cntw[delta]; cntw[delta] = prev + __popc(grp); }
-                        prev = __shfl_sync(0xffffffffu, prev, leader);
-                        *ij = wd | (prev + __popc(grp & lt));
-                        __syncwarp();
-                        ij += 40; pj += 32;
+                    } else {
+#pragma unroll 1
+                        for (int k = 0; k < SE_PPT; k++)
+                            S.info[info_index(j0) + k] = classify_any(pb, (int)(j0 + k), i0 + k, w, a.npix, plane);
+                    }
+                }
+                __syncwarp();
+                // rank: lane = pixel, 32 consecutive pixels per step: the stable rank of an out-of-range pixel among the warp's
+                // pixels of its context is one match over the warp (pixels that are not coded out of range get a key of their
+                // own: a group of one, nothing counted) and one counter per context
+                {
+                    uint32_t *ij = &S.info[info_index(wp0 + lane)];          // info_index advances by 40 words per 32 pixels
+#pragma unroll 1
+                    for (int s0 = 0; s0 < SE_WSTEPS; s0 += 4, ij += 160) {
+                        // four steps at a time: the matches are issued back to back (their latency is long), the counters follow in order
+                        uint32_t wd[4], grp[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) wd[u] = ij[40 * u];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) grp[u] = __match_any_sync(0xffffffffu, (wd[u] >> 31) ? (wd[u] >> 12) & 255u : 256u);   // one group for all the others: the match costs by distinct keys
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const bool oor = wd[u] >> 31;
+                            const uint32_t delta = (wd[u] >> 12) & 255u;
+                            const int leader = __ffs(grp[u]) - 1;
+                            uint32_t prev = 0;
+                            if (oor && (int)lane == leader) { prev = cntw[delta]; cntw[delta] = prev + __popc(grp[u]); }
+                            prev = __shfl_sync(0xffffffffu, prev, leader);
+                            if (oor) ij[40 * u] = wd[u] | (prev + __popc(grp[u] & lt));
+                            __syncwarp();
+                        }
                     }
                 }
                 // bases of the warp's segments: exclusive prefix of the counts, every segment padded to a multiple of four
