@@ -643,21 +643,20 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
             // the walk is over: its segment tables become the bit window (zeroed here, filled after the next barrier)
             for (uint32_t i = tid; i < SE_OUT_WORDS + 4; i += SE_THREADS) out[i] = 0u;
 
-            // ---- code: 16 consecutive pixels per thread, records stay in registers -------------------------------
-            uint32_t r[SE_PPT];
+            // ---- code: 16 consecutive pixels per thread, four at a time; the records take the place of the info words -------
             uint32_t mylen = 0;
+            uint4 *const iw = reinterpret_cast<uint4 *>(&S.info[info_index(tid * SE_PPT)]);   // my 16 words are contiguous
             {
-                const uint4 *iw = reinterpret_cast<const uint4 *>(&S.info[info_index(tid * SE_PPT)]);
                 const uint8_t *ecw = S.ec[tid >> 5];   // the warp region my 16 pixels were grouped into: (16 * tid) / 512
-#pragma unroll
+#pragma unroll 1
                 for (int q = 0; q < SE_PPT / 4; q++) {
                     const uint4 v = iw[q];
-                    if (a.dbg & 2u) { r[4 * q] = r[4 * q + 1] = r[4 * q + 2] = r[4 * q + 3] = (v.x & 1u) << 22; continue; }
-                    r[4 * q] = make_record(v.x, ecw); r[4 * q + 1] = make_record(v.y, ecw);
-                    r[4 * q + 2] = make_record(v.z, ecw); r[4 * q + 3] = make_record(v.w, ecw);
+                    uint4 r;
+                    if (a.dbg & 2u) { r.x = r.y = r.z = r.w = (v.x & 1u) << 22; }
+                    else { r.x = make_record(v.x, ecw); r.y = make_record(v.y, ecw); r.z = make_record(v.z, ecw); r.w = make_record(v.w, ecw); }
+                    mylen += rec_len(r.x) + rec_len(r.y) + rec_len(r.z) + rec_len(r.w);
+                    iw[q] = r;
                 }
-#pragma unroll
-                for (int q = 0; q < SE_PPT; q++) mylen += rec_len(r[q]);
             }
             uint32_t inc = mylen;
 #pragma unroll
@@ -683,27 +682,32 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 // one window: my codes are concatenated in registers and leave as whole words (atomicOr: the first and the last
                 // word of my range are shared with my neighbours; about two words per thread and band)
                 uint32_t wi = pos >> 5, sh = pos & 31u, wv = 0;
+#pragma unroll 1
+                for (int q = 0; q < SE_PPT / 4; q++) {
+                    const uint4 r4 = iw[q];
+                    const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-                for (int q = 0; q < SE_PPT; q++) {
-                    const uint32_t len = rec_len(r[q]);
-                    if (len > (uint32_t)REC_SHORT_MAX) {
-                        // long unary run: my partial word first, then field by field
-                        if (wv) atomicOr(&out[wi], wv);
-                        const uint32_t at = (wi << 5) + sh;
-                        pack_long(out, r[q], at);
-                        const uint32_t np2 = at + len;
-                        wi = np2 >> 5; sh = np2 & 31u; wv = 0;
-                        continue;
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t len = rec_len(r[k]);
+                        if (len > (uint32_t)REC_SHORT_MAX) {
+                            // long unary run: my partial word first, then field by field
+                            if (wv) atomicOr(&out[wi], wv);
+                            const uint32_t at = (wi << 5) + sh;
+                            pack_long(out, r[k], at);
+                            const uint32_t np2 = at + len;
+                            wi = np2 >> 5; sh = np2 & 31u; wv = 0;
+                            continue;
+                        }
+                        const uint32_t left = ((r[k] & 0x3fffffu) << 1) << (31u - len);   // code word, MSB aligned (nothing for len 0)
+                        wv |= left >> sh;
+                        const uint32_t nsh = sh + len;
+                        if (nsh >= 32u) {                                                  // the word is full: sh >= 10 here
+                            atomicOr(&out[wi], wv);
+                            wi++;
+                            wv = left << (32u - sh);
+                        }
+                        sh = nsh & 31u;
                     }
-                    const uint32_t left = ((r[q] & 0x3fffffu) << 1) << (31u - len);   // code word, MSB aligned (nothing for len 0)
-                    wv |= left >> sh;
-                    const uint32_t nsh = sh + len;
-                    if (nsh >= 32u) {                                                  // the word is full: sh >= 10 here
-                        atomicOr(&out[wi], wv);
-                        wi++;
-                        wv = left << (32u - sh);
-                    }
-                    sh = nsh & 31u;
                 }
                 if (wv) atomicOr(&out[wi], wv);
                 __syncthreads();
@@ -715,12 +719,8 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
                 carry = out[nfull];
                 wpos += nfull;
             } else {
-                // more than 16 bits per pixel (rare): the records go to shared memory (the info words are dead) and the band leaves
-                // through several windows, out of line
-                uint32_t *recs = &S.info[tid * SE_PPT];
-#pragma unroll
-                for (int q = 0; q < SE_PPT; q++) recs[q] = r[q];
-                pack_windows(out, recs, pos, win_bits, slot, slot_words, wpos, carry, ovf);
+                // more than 16 bits per pixel (rare): the band leaves through several windows, out of line
+                pack_windows(out, reinterpret_cast<const uint32_t *>(iw), pos, win_bits, slot, slot_words, wpos, carry, ovf);
             }
             carrybits = win_bits & 31u;
             total_bits += band_bits;
