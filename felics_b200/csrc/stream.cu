@@ -153,7 +153,7 @@ __device__ __forceinline__ uint32_t make_info(int p, int v1, int v2) {
     const int m = max(below, above);
     const uint32_t val = (uint32_t)(m >= 0 ? m : p - l);
     const uint32_t top = (~(uint32_t)(below & above) & 0x80000000u) | ((~(uint32_t)above >> 1) & 0x40000000u);   // [31] out of range, [30] above
-    return top | (val << 21) | ((uint32_t)(h - l) << 12);
+    return top + val * 0x200000u + (uint32_t)(h - l) * 0x1000u;   // disjoint fields: sums the compiler can turn into multiply-adds (the ALU pipe is the busy one)
 }
 // any pixel (misc.rs:6-24): steps that touch a row start, the first row or the end of the image; pb = first pixel of the band,
 // j = offset in the band, i = index in the plane
@@ -344,7 +344,7 @@ __device__ __forceinline__ uint32_t make_record(uint32_t wd, const uint8_t *ecw)
     const uint32_t len = q + k + 3u;
     const uint32_t ones = ((top - 1u) << min(q, 24u)) - 1u;   // above: q + 1 ones, the top one is the `above` bit; below: q ones
     const uint32_t rshort = (len << 22) | (ones << (k + 1u)) | rem;
-    const uint32_t rlong = (len << 22) | ((top & 1u) << 12) | (k << 9) | val;
+    const uint32_t rlong = len * 0x400000u + (top & 1u) * 0x1000u + k * 0x200u + val;
     const uint32_t roor = len <= (uint32_t)REC_SHORT_MAX ? rshort : rlong;
     const uint32_t r = oor ? roor : rin;
     return top == 1u ? 0u : r;
