@@ -406,6 +406,8 @@ def test_sidecar_round_trip(codec):
         (rng.integers(0, 256, (260, 4096), dtype=np.uint8), 2),                 # noise, one row pair per band
         (np.stack([gnat_image(768, 400, seed=s) for s in (3, 4, 5)], axis=-1), 16),   # RGB: bands of three planes
         (gnat_image(333, 200), 0),                                              # odd width: one band per plane only
+        (np.stack([gnat_image(333, 200, seed=s) for s in (6, 7, 8)], axis=-1), 0),    # RGB of odd width: three entries whose rows are not a multiple of eight bytes
+        (gnat_image(334, 4100), 2048),                                          # width = 2 mod 4 with two bands per plane
         (np.clip(128 + rng.normal(0, 1.2, (2048, 1024)), 0, 255).astype(np.uint8), 32),   # long chains with many halvings before each band
         (gnat_image(2048, 2048), 64),                                           # speculation, hops and serial walk all feed the snapshots
     ]
