@@ -455,7 +455,7 @@ def run_tiles(args, rig):
         pin_in.copy_(d_in[:e2e_tiles * tile_px])
         host_offsets = np.zeros(e2e_tiles + 1, dtype=np.uint64)
         e2e_steps = args.steps if e2e_tiles * tile_px <= (4 << 30) else min(args.steps, 3)
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(max(1, min(args.warmup, 3))):
             encode_host_call(rig, e2e_tiles, pin_in, chdr, pin_out, pin_out.numel(), host_offsets)
         rig.barrier()
         ms_e2e = rig.timed(lambda: encode_host_call(rig, e2e_tiles, pin_in, chdr, pin_out, pin_out.numel(), host_offsets), e2e_steps)
