@@ -1388,7 +1388,19 @@ int encode_batch_device(felics_ctx *ctx, size_t n, const void *d_pixels, const f
 
     // images per sub-batch: bound scratch (and keep every global element index below 2^32)
     size_t per_image = carve(nullptr, g, 1).bytes;
+    // the walk of a sub-batch has one warp per chain and is bound by latency: the more images travel together, the better
+    // the machine is filled, so the scratch budget is half of what the device has free (the context's own scratch counted as
+    // free), between 12 and 48 GB
     size_t budget = (size_t)12 << 30;
+    if (n > 1 && per_image * n > budget) {
+        if (!ctx->batch_budget) {   // asked once per context: the query itself takes milliseconds
+            size_t free_b = 0, total_b = 0;
+            ctx->batch_budget = budget;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                ctx->batch_budget = std::min<size_t>((size_t)48 << 30, std::max<size_t>(budget, (free_b + ctx->scratch_cap) / 2));
+        }
+        budget = ctx->batch_budget;
+    }
     size_t sub = std::max<size_t>(1, std::min<size_t>(n, budget / std::max<size_t>(per_image, 1)));
     while (sub > 1 && (uint64_t)sub * g.nch * g.cap >= 0xffff0000ull) sub--;
     if ((uint64_t)g.nch * g.cap >= 0xffff0000ull) {
