@@ -601,15 +601,14 @@ __global__ void __launch_bounds__(32 * G8_WARPS) k_decode_g8(G8Args a, uint32_t 
             const uint32_t ctx = (uint32_t)(hi - lo);                          // <= 255: every sample so far is 0..255
             const uint32_t top = br.peek32();
             int value;
+            int used;   // bits of this pixel's code still to be skipped: one skip and one refill, behind the two classes
             if (top >> 31) {                                                    // InRange (:208-215)
                 const uint32_t nn = ctx + 1;
                 const int m = 31 - __clz(nn);
                 const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
                 uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;               // marker + m bits (+ 1): at most 10 bits, all inside the window
-                int used = 1 + m;
+                used = 1 + m;
                 if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
-                br.skip(used);
-                br.refill();
                 xx += left_p;                                                   // rotate_left (:55-57); xx < nn before
                 if (xx >= nn) xx -= nn;
                 value = lo + (int)xx;
@@ -622,17 +621,30 @@ __global__ void __launch_bounds__(32 * G8_WARPS) k_decode_g8(G8Args a, uint32_t 
                     r.w &= 255u;
                 }
                 const uint32_t k = r.w;                                         // get_k (:202), computed when the row was last updated
-                br.skip(2);
-                br.refill();
-                uint32_t q = 0;                                                 // read_unary0
-                for (;;) {
-                    const uint32_t ones = __clz(~br.peek32());                  // 32 when all ones
-                    if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
-                    q += 32; br.skip(32); br.refill();
-                    if (br.eof() || q > 255u) break;
+                const uint32_t rest = top << 2;                                 // the bits behind the two markers
+                const uint32_t ones = __clz(~rest);                             // the unary run, as far as the window shows it (at most 30)
+                uint32_t q, rem;
+                if (ones + k + 3u <= 32u) {
+                    // the whole code lies in the window: two markers, `ones` ones, a zero, k remainder bits
+                    q = ones;
+                    rem = k ? (rest << (ones + 1u)) >> (32u - k) : 0u;
+                    used = (int)(3u + ones + k);
+                    if (br.used + (uint32_t)used > br.limit) { st = FELICS_ERR_IO; return 0; }
+                } else {
+                    // a long run: word by word (read_unary0, then the remainder)
+                    br.skip(2);
+                    br.refill();
+                    q = 0;
+                    for (;;) {
+                        const uint32_t o2 = __clz(~br.peek32());                // 32 when all ones
+                        if (o2 < 32) { q += o2; br.skip((int)o2 + 1); br.refill(); break; }
+                        q += 32; br.skip(32); br.refill();
+                        if (br.eof() || q > 255u) break;
+                    }
+                    rem = br.read((int)k);
+                    used = 0;
+                    if (br.eof()) { st = FELICS_ERR_IO; return 0; }
                 }
-                const uint32_t rem = br.read((int)k);
-                if (br.eof()) { st = FELICS_ERR_IO; return 0; }
                 const uint32_t e = (q << k) + rem;
                 if (q > 255u || e > 255u) { st = FELICS_NEED_EXACT; return 0; }
                 // update (parameter_selection.rs:49-65) on u16 pairs: cost of e under k = (e >> k) + 1 + k
@@ -648,6 +660,8 @@ __global__ void __launch_bounds__(32 * G8_WARPS) k_decode_g8(G8Args a, uint32_t 
                 *rowp = r;
                 value = above ? hi + (int)e + 1 : lo - (int)e - 1;              // (:216-243)
             }
+            br.skip(used);
+            br.refill();
             if ((uint32_t)value > 255u) st = FELICS_NEED_EXACT;
             return value;
         };
