@@ -382,16 +382,15 @@ __device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t
                 if (ctx > 510u) { st = FELICS_ERR_CORRUPT; break; }   // assert!(context <= max_context), parameter_selection.rs:72
                 const uint32_t top = br.peek32();
                 int value;
+                int used;   // bits of this pixel's code still to be skipped: one skip and one refill, behind the two classes
                 if (top >> 31) {                                        // InRange (:208-215)
                     const uint32_t nn = ctx + 1;
                     const int m = 31 - __clz(nn);
                     const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
                     // marker + m bits (+ 1): at most 11 bits, all inside the window
                     uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;
-                    int used = 1 + m;
+                    used = 1 + m;
                     if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
-                    br.skip(used);
-                    br.refill();
                     xx += left_p;                                       // rotate_left (:55-57)
                     if (xx >= nn) xx -= nn;
                     if (xx >= nn) { st = FELICS_ERR_CORRUPT; break; }
@@ -401,19 +400,32 @@ __device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t
                     uint32_t *row = tab + ctx * NK;
                     const uint2 r01 = *reinterpret_cast<const uint2 *>(row), r23 = *reinterpret_cast<const uint2 *>(row + 2), r45 = *reinterpret_cast<const uint2 *>(row + 4);
                     uint32_t rr[NK] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y};
-                    const int k = argmin_last(rr);                      // get_k (:202)
-                    br.skip(2);
-                    br.refill();
-                    uint32_t q = 0;                                     // read_unary0
-                    for (;;) {
-                        const uint32_t ones = __clz(~br.peek32());      // 32 when all ones
-                        if (ones < 32) { q += ones; br.skip((int)ones + 1); br.refill(); break; }
-                        q += 32; br.skip(32); br.refill();
-                        if (br.eof()) break;
+                    const uint32_t k = (uint32_t)argmin_last(rr);       // get_k (:202)
+                    const uint32_t rest = top << 2;                     // the bits behind the two markers
+                    const uint32_t ones = __clz(~rest);                 // the unary run, as far as the window shows it (at most 30)
+                    uint32_t q, rem;
+                    if (ones + k + 3u <= 32u) {
+                        // the whole code lies in the window: two markers, `ones` ones, a zero, k remainder bits
+                        q = ones;
+                        rem = k ? (rest << (ones + 1u)) >> (32u - k) : 0u;
+                        used = (int)(3u + ones + k);
+                        if (br.used + (uint32_t)used > br.limit) { st = FELICS_ERR_IO; break; }
+                    } else {
+                        // a long run: word by word (read_unary0, then the remainder)
+                        br.skip(2);
+                        br.refill();
+                        q = 0;
+                        for (;;) {
+                            const uint32_t o2 = __clz(~br.peek32());    // 32 when all ones
+                            if (o2 < 32) { q += o2; br.skip((int)o2 + 1); br.refill(); break; }
+                            q += 32; br.skip(32); br.refill();
+                            if (br.eof()) break;
+                        }
+                        rem = br.read((int)k);
+                        used = 0;
+                        if (br.eof()) { st = FELICS_ERR_IO; break; }
+                        if (q > 70000u) { st = FELICS_NEED_EXACT; break; }
                     }
-                    const uint32_t rem = br.read(k);
-                    if (br.eof()) { st = FELICS_ERR_IO; break; }
-                    if (q > 70000u) { st = FELICS_NEED_EXACT; break; }
                     const uint32_t e = (q << k) + rem;
                     uint32_t mn = 0xffffffffu;
 #pragma unroll
@@ -430,6 +442,8 @@ __device__ __forceinline__ int decode_rows(BitWindow &br, uint32_t *tab, int16_t
                     *reinterpret_cast<uint2 *>(row + 4) = make_uint2(rr[4], rr[5]);
                     value = above ? hi + (int)e + 1 : lo - (int)e - 1;  // (:216-243)
                 }
+                br.skip(used);
+                br.refill();
                 if (value < -32768 || value > 32767) { st = FELICS_NEED_EXACT; break; }
                 cur[x] = (int16_t)value;
                 left = value;
