@@ -614,19 +614,21 @@ __global__ void __launch_bounds__(32 * G8_WARPS) k_decode_g8(G8Args a, uint32_t 
             const int hi = max(v1, v2), lo = min(v1, v2);
             const uint32_t ctx = (uint32_t)(hi - lo);                          // <= 255: every sample so far is 0..255
             const uint32_t top = br.peek32();
-            int value;
-            int used;   // bits of this pixel's code still to be skipped: one skip and one refill, behind the two classes
-            if (top >> 31) {                                                    // InRange (:208-215)
+            // the in-range reading of the window (phase_in_coding.rs:102-109, :55-57) is computed for every lane: it is short, and
+            // the lanes whose pixel is out of range then go through their branch alone instead of waiting for this one first
+            int value, used;
+            {
                 const uint32_t nn = ctx + 1;
                 const int m = 31 - __clz(nn);
                 const uint32_t left_p = nn - (1u << m), right_p = (2u << m) - nn;
                 uint32_t xx = m ? ((top << 1) >> (32 - m)) : 0u;               // marker + m bits (+ 1): at most 10 bits, all inside the window
                 used = 1 + m;
-                if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }   // phase_in_coding.rs:102-109
-                xx += left_p;                                                   // rotate_left (:55-57); xx < nn before
+                if (xx >= right_p) { xx = (xx - right_p) * 2 + right_p + ((top >> (30 - m)) & 1u); used++; }
+                xx += left_p;                                                   // rotate_left; xx < nn before
                 if (xx >= nn) xx -= nn;
                 value = lo + (int)xx;
-            } else {
+            }
+            if (!(top >> 31)) {                                                 // not InRange (:216-243)
                 const uint32_t above = (top >> 30) & 1u;
                 uint4 *rowp = ctx < (uint32_t)HOT ? mytab + ctx * F : mycold + (ctx - HOT);
                 uint4 r = *rowp;
