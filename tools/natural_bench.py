@@ -12,7 +12,9 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4736
 img = dict(np.load(Path(__file__).resolve().parents[1] / "tests/golden/images.npz"))["gray8_boat.512"]
 dev = torch.device("cuda", 0)
 codec = fb.Codec(device=0)
-codec.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+stream = torch.cuda.Stream(dev)
+torch.cuda.set_stream(stream)
+codec.set_stream(stream.cuda_stream)   # one explicit stream for torch and the codec (handle 0 would mean the codec's own)
 d_in = torch.from_numpy(img).to(dev).reshape(1, -1).repeat(n, 1).contiguous()
 hdr = fb._header_of(img)
 cap = d_in.numel() + 4096 * n
