@@ -40,7 +40,10 @@ namespace felics {
 
 namespace {
 
-constexpr int SE_THREADS = 256;
+#ifndef SE_THREADS_N
+#define SE_THREADS_N 256
+#endif
+constexpr int SE_THREADS = SE_THREADS_N;
 #ifndef SE_CTAS_PER_SM
 #define SE_CTAS_PER_SM 4
 #endif
@@ -52,7 +55,7 @@ constexpr int SE_WSTEPS = SE_WPIX / 32;
 constexpr int SE_INFO_WORDS = SE_BAND + SE_BAND / 16 * 4;   // one word per pixel, 4 words of padding per 16 (bank spread)
 constexpr int SE_NCTX = 256;                                // contexts of 8-bit gray samples: H - L <= 255
 constexpr int SE_WREG = SE_WPIX + 3 * SE_NCTX;              // bytes of a warp's region of the chain array (segments are padded to 4)
-constexpr int SE_OUT_WORDS = 2048;                          // bit window: 65536 bits = 16 bits per pixel of a band
+constexpr int SE_OUT_WORDS = SE_BAND / 2;                    // bit window: 16 bits per pixel of a band
 constexpr uint32_t SE_LONG = 32;                            // chains this long (padded, per band) are walked in 128-element steps
 constexpr uint32_t SE_HALVE_KEY = (HALVE_AT + 1u) << 3;     // key of a count that has passed 1024
 constexpr uint32_t SE_NONE = 0xFFFFFFFFu;
@@ -73,7 +76,7 @@ struct SeSmem {
     uint32_t lut45[SE_NCTX];            // ... under k = 4, 5
     uint16_t longc[SE_NCTX];            // long chains of the band: context | steps << 8
     uint16_t shortlist[SE_NCTX];
-    uint32_t roundcnt[40];              // chains that have a step s (a chain of a band has at most 34 steps)
+    uint32_t roundcnt[SE_BAND / 128 + 8];   // chains that have a step s (a chain of a band has at most SE_BAND / 128 + 2 steps)
     uint8_t ec[SE_WARPS][SE_WREG];      // residuals grouped by context, one region per warp; the walk overwrites them with k
     uint32_t wsum[SE_WARPS];
     uint32_t ntask, nlong, nshort, task, plane;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
             if (b + 1 < nbands)
                 load_band(pixbuf0 + ((b + 1) & 1u) * buf_bytes, a, plane, start + SE_BAND, min((uint32_t)SE_BAND, a.npix - start - SE_BAND), &S.bar[(b + 1) & 1u]);
             if (tid == 0) { S.ntask = 0; S.nlong = 0; S.nshort = 0; S.task = 0; }
-            if (tid < 40) S.roundcnt[tid] = 0u;
+            if (tid < (uint32_t)(SE_BAND / 128 + 8)) S.roundcnt[tid] = 0u;
 
             // ---- group: classify, rank and scatter, every warp on its own 512 pixels --------------------------------
             if (!(a.dbg & 4u)) {
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(SE_THREADS, SE_CTAS_PER_SM) k_stream_encode(St
             SE_CLK(1);
 
             // ---- chains: one thread per context: length of its chain in this band, work lists -------------------------
-            if (!(a.dbg & 4u)) {
+            if (!(a.dbg & 4u) && tid < (uint32_t)SE_NCTX) {
                 uint32_t vlen = 0;
 #pragma unroll
                 for (int q = 0; q < SE_WARPS; q++) vlen += ((S.wseg[q][tid] & 0xffffu) + 3u) & ~3u;
