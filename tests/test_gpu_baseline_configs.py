@@ -131,3 +131,17 @@ def test_mixed_batch_reports_per_image_errors(codec):
 def test_empty_mixed_batch(codec):
     arena, offsets = codec.compress_many([])
     assert len(arena) == 0 and list(offsets) == [0]
+
+
+def test_mixed_batch_larger_than_one_chunk(codec):
+    # felics_*_batch_v move the images in chunks of about 1 GiB of pixels: eight big images (1.15 GB) of two shapes cross the
+    # boundary, the groups of the two chunks interleave; two distinct images keep the oracle's share short (the decoder's side of
+    # the chunking runs at small scale in the tests above: a big image decodes for tens of seconds)
+    rgb = gnat_rgb(8192, 8192)
+    gray = gnat_image(8192, 8192, seed=9)
+    order = [rgb, gray, rgb, gray, rgb, rgb, gray, rgb]
+    want = {id(rgb): fo.compress(rgb), id(gray): fo.compress(gray)}
+    arena, offsets = codec.compress_many(order)
+    for i, img in enumerate(order):
+        assert bytes(arena[int(offsets[i]):int(offsets[i + 1])]) == want[id(img)], i
+    assert int(offsets[-1]) == 5 * len(want[id(rgb)]) + 3 * len(want[id(gray)])
