@@ -138,6 +138,8 @@ int felics_ctx_create(int device, felics_ctx **out) {
         if (ng8 && ng8[0] == '1') ctx->no_g8 = true;
         const char *g8f = getenv("FELICS_B200_G8_FILES");    // experiment switch: files per warp of the gray batch decoder (1, 2, 4, 8)
         if (g8f) { const int f = atoi(g8f); if (f == 1 || f == 2 || f == 4 || f == 8 || f == 16 || f == 32) ctx->g8_files_per_warp = f; }
+        const char *vch = getenv("FELICS_B200_V_CHUNK_KB");  // test switch: transfer chunk of the mixed-shape batch calls (default 1 GiB)
+        if (vch && atol(vch) > 0) ctx->v_chunk_bytes = (size_t)atol(vch) << 10;
         const char *nst = getenv("FELICS_B200_NO_STREAM");   // debug/bench switch: gray batches through the multi-kernel pipeline
         ctx->no_stream = nst && nst[0] == '1';
         const char *sdbg = getenv("FELICS_B200_STREAM_DBG");
@@ -354,7 +356,7 @@ int felics_compress_batch_v(felics_ctx *ctx, size_t n, const void *const *pixels
         if (!pixels[i] && felics_pixel_bytes(&hdrs[i])) { set_error("null pixels for image %zu", i); return FELICS_ERR_INVALID_ARGUMENT; }
     }
     cudaStream_t st = ctx->stream;
-    const size_t chunk_bytes = (size_t)1 << 30;
+    const size_t chunk_bytes = ctx->v_chunk_bytes;
     bool too_small = false;
     struct Group { felics_header hdr; std::vector<size_t> idx; size_t in_base, out_base, out_cap; std::vector<uint64_t> off; std::vector<uint8_t> bounce; };
     for (size_t c0 = 0; c0 < n;) {
@@ -453,7 +455,7 @@ int felics_decompress_batch_v(felics_ctx *ctx, size_t n, const uint8_t *arena, c
         if (felics_pixel_bytes(&hs[i]) > caps[i]) { status[i] = FELICS_ERR_BUFFER_TOO_SMALL; continue; }
         ok[i] = 1;
     }
-    const size_t chunk_bytes = (size_t)1 << 30;
+    const size_t chunk_bytes = ctx->v_chunk_bytes;
     struct Group { felics_header hdr; std::vector<size_t> idx; std::vector<uint64_t> off; size_t in_base, out_base; };
     for (size_t c0 = 0; c0 < n;) {
         size_t c1 = c0, bytes = 0;

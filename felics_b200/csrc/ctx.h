@@ -61,6 +61,7 @@ struct felics_ctx {
     void *scratch = nullptr;      // device scratch, grown on demand
     size_t scratch_cap = 0;
     size_t batch_budget = 0;      // scratch budget of batches through the multi-kernel pipeline (0 = not yet asked)
+    size_t v_chunk_bytes = (size_t)1 << 30;   // pixels per transfer chunk of the mixed-shape batch calls
     void *v_in = nullptr;         // device buffers of the mixed-shape batch calls (felics_*_batch_v)
     size_t v_in_cap = 0;
     void *v_out = nullptr;

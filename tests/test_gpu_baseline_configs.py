@@ -145,3 +145,29 @@ def test_mixed_batch_larger_than_one_chunk(codec):
     for i, img in enumerate(order):
         assert bytes(arena[int(offsets[i]):int(offsets[i + 1])]) == want[id(img)], i
     assert int(offsets[-1]) == 5 * len(want[id(rgb)]) + 3 * len(want[id(gray)])
+
+
+def test_mixed_batch_in_many_small_chunks(monkeypatch):
+    # the same chunking with a 64 KB chunk (test switch): 60 small images of four pixel types fall into about twenty chunks,
+    # both ways
+    monkeypatch.setenv("FELICS_B200_V_CHUNK_KB", "64")
+    rng = np.random.default_rng(23)
+    images = []
+    for i in range(60):
+        h, w = int(rng.integers(8, 120)), int(rng.integers(8, 120))
+        if i % 4 == 0:
+            images.append(rng.integers(100, 140, (h, w), dtype=np.uint8))
+        elif i % 4 == 1:
+            images.append(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        elif i % 4 == 2:
+            images.append(rng.integers(2000, 2300, (h, w), dtype=np.uint16))
+        else:
+            images.append(images[i - 3].copy())          # shapes that come back in a later chunk
+    with felics_b200.Codec(device=0) as c:
+        arena, offsets = c.compress_many(images)
+        for i, img in enumerate(images):
+            assert bytes(arena[int(offsets[i]):int(offsets[i + 1])]) == fo.compress(img), i
+        outs, status = c.decompress_many(arena, offsets)
+    assert not status.any()
+    for o, img in zip(outs, images):
+        assert o.dtype == img.dtype and np.array_equal(o, img)
